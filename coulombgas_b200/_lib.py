@@ -1,0 +1,53 @@
+"""ctypes binding of libcgb200.so (include/cgb200.h).  There is no fallback: if the CUDA library has not
+been built (python __graft_entry__.py / make -C coulombgas_b200/csrc) importing this module raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcgb200.so")
+
+NPARAMS = 1074
+MAX_N = 64
+
+
+class CgbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "coulombgas_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C coulombgas_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, f64, u64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_size_t
+    pd2 = ctypes.POINTER(ctypes.c_double)
+    lib.cgb_abi_version.restype = i32
+    lib.cgb_error_string.restype = ctypes.c_char_p
+    lib.cgb_error_string.argtypes = [i32]
+    lib.cgb_ktable_twist_host.argtypes = [vp, i32, pd2]
+    lib.cgb_ewald_prepare_host.argtypes = [vp, i32, f64, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    lib.cgb_logp_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
+    lib.cgb_mcmc_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
+    lib.cgb_logp_f64io.argtypes = [vp, vp, vp, vp, i32, pd2, vp, i32, i32, f64, vp, vp, vp, vp, sz]
+    lib.cgb_mcmc_sweep_f64io.argtypes = [vp, vp, vp, vp, i32, pd2, vp, vp, vp, u64, i32, f64, f64, i32, i32, i32,
+                                         vp, vp, vp, vp, vp, sz]
+    lib.cgb_ewald_f64io.argtypes = [vp, vp, i32, i32, f64, f64, f64, vp, i32, i32, vp]
+    lib.cgb_microbench.argtypes = [vp, i32, i32, i32, vp]
+    for f in ("cgb_ktable_twist_host", "cgb_ewald_prepare_host", "cgb_logp_workspace_bytes",
+              "cgb_mcmc_workspace_bytes", "cgb_logp_f64io", "cgb_mcmc_sweep_f64io", "cgb_ewald_f64io",
+              "cgb_microbench"):
+        getattr(lib, f).restype = i32
+    return lib
+
+
+lib = _load()
+
+EXPORTS = ("cgb_abi_version", "cgb_error_string", "cgb_ktable_twist_host", "cgb_ewald_prepare_host",
+           "cgb_logp_workspace_bytes", "cgb_mcmc_workspace_bytes", "cgb_logp_f64io", "cgb_mcmc_sweep_f64io",
+           "cgb_ewald_f64io", "cgb_microbench")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise CgbError("%s failed: %s (code %d)" % (what, lib.cgb_error_string(rc).decode(), rc))

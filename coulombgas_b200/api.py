@@ -1,0 +1,343 @@
+"""Host-side mirror of the reference's hot-path interface (same names, argument order and meaning),
+dispatching to the C ABI of libcgb200.so.  Reference file:line citations are relative to the reference tree.
+
+Arrays: torch CUDA float64 tensors are used in place (zero copy; results are CUDA tensors on the current
+stream); NumPy arrays are copied host->device->host around the call (results are NumPy).  Everything is
+float64 at the boundary, as in the reference (main.py:2-3 enables x64)."""
+import ctypes
+import dataclasses
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, NPARAMS
+
+# ----------------------------------------------------------------------------------------------------
+# parameters / tables
+# ----------------------------------------------------------------------------------------------------
+_ORDER = ("fermi_net/~/linear_2", "fermi_net/~/linear", "fermi_net/~/linear_1", "fermi_net/linear")
+_SHAPES = ((5, 16), (9, 16), (48, 16), (16, 2))
+
+
+def pack_params(params_flow):
+    """haiku dict {module: {"w","b"}} of FermiNet(depth=2, spsize=16, tpsize=16), dim 2 (src/flow.py:5-14,54;
+    SURVEY §8 a13) -> flat float64 vector [Wt,bt,W0,b0,W1,b1,Wf,bf] (include/cgb200.h).  A flat vector of
+    length 1074 (NumPy or torch) passes through."""
+    if isinstance(params_flow, torch.Tensor):
+        if params_flow.numel() != NPARAMS:
+            raise ValueError("flat flow parameter vector must have %d entries" % NPARAMS)
+        return params_flow.reshape(-1).to(torch.float64)
+    if isinstance(params_flow, np.ndarray):
+        if params_flow.size != NPARAMS:
+            raise ValueError("flat flow parameter vector must have %d entries" % NPARAMS)
+        return np.ascontiguousarray(params_flow.reshape(-1), dtype=np.float64)
+    if set(params_flow.keys()) != set(_ORDER):
+        raise ValueError("unsupported flow: expected depth=2 FermiNet modules %s, got %s"
+                         % (sorted(_ORDER), sorted(params_flow.keys())))
+    parts = []
+    for name, shape in zip(_ORDER, _SHAPES):
+        w, b = np.asarray(params_flow[name]["w"], dtype=np.float64), np.asarray(params_flow[name]["b"], dtype=np.float64)
+        if w.shape != shape or b.shape != (shape[1],):
+            raise ValueError("unsupported flow shape for %s: w %s b %s (need spsize=tpsize=16, dim=2)"
+                             % (name, w.shape, b.shape))
+        parts += [w.ravel(), b.ravel()]
+    return np.concatenate(parts)
+
+
+def kpoints(dim, Gmax):
+    """src/potential.py:7-17 — host table builder (integer G, 0 < |G|^2 <= Gmax^2, meshgrid order)."""
+    rng = np.arange(-Gmax, Gmax + 1)
+    grids = np.meshgrid(*([rng] * dim))
+    G = np.array([g.flatten() for g in grids]).T
+    G2 = (G ** 2).sum(axis=-1)
+    return G[(G2 <= Gmax ** 2) * (G2 > 0)]
+
+
+def madelung(dim, kappa, G):
+    """src/potential.py:19-34 (dim 2 branch) — host, once per run (main.py:171)."""
+    if dim != 2:
+        raise NotImplementedError("only dim=2 is supported")
+    import math
+    Gn = np.linalg.norm(np.asarray(G, dtype=np.float64), axis=-1)
+    g_k = np.array([math.erfc(math.pi * g / kappa) / g for g in Gn])
+    return float(g_k.sum() - 2 * math.sqrt(math.pi) / kappa - 2 * kappa / math.sqrt(math.pi))
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.CgbError("coulombgas_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _to_dev(a, dtype):
+    """-> (contiguous CUDA tensor, was_numpy)"""
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            return a.to(_dev(), dtype).contiguous(), False
+        if a.dtype != dtype or not a.is_contiguous():
+            a = a.to(dtype).contiguous()
+        return a, False
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(_dev(), non_blocking=False), True
+
+
+# ----------------------------------------------------------------------------------------------------
+# logp
+# ----------------------------------------------------------------------------------------------------
+class Logp:
+    """The callable returned by make_logp: logp(x, params, state_idx) -> (batch,)  (src/logpsi.py:176-179)."""
+
+    def __init__(self, sp_indices, L):
+        kt = np.ascontiguousarray(np.asarray(sp_indices, dtype=np.float64))
+        if kt.ndim != 2 or kt.shape[1] != 2:
+            raise ValueError("sp_indices must be (num_states, 2): only dim=2 is supported")
+        tw = (ctypes.c_double * 2)()
+        check(lib.cgb_ktable_twist_host(kt.ctypes.data_as(ctypes.c_void_p), kt.shape[0], tw), "cgb_ktable_twist_host")
+        self.ktable_host, self.M, self.L = kt, kt.shape[0], float(L)
+        self.twist = tw
+        self._ktable_dev = {}
+        self._ws = {}
+
+    def ktable_dev(self):
+        d = torch.cuda.current_device()
+        if d not in self._ktable_dev:
+            self._ktable_dev[d] = torch.as_tensor(self.ktable_host).to(_dev())
+        return self._ktable_dev[d]
+
+    def workspace(self, B, n):
+        d = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        if d not in self._ws:
+            nbytes = ctypes.c_size_t()
+            check(lib.cgb_logp_workspace_bytes(B, n, ctypes.byref(nbytes)), "cgb_logp_workspace_bytes")
+            self._ws[d] = torch.empty(nbytes.value, dtype=torch.uint8, device=_dev())
+        return self._ws[d]
+
+    def __call__(self, x, params, state_idx, return_parts=False, return_jac=False):
+        xd, was_np = _to_dev(x, torch.float64)
+        if xd.ndim != 3 or xd.shape[2] != 2:
+            raise ValueError("x must be (batch, n, 2)")
+        B, n = int(xd.shape[0]), int(xd.shape[1])
+        pd, _ = _to_dev(pack_params(params), torch.float64)
+        sd, _ = _to_dev(state_idx, torch.int32)
+        if tuple(sd.shape) != (B, n):
+            raise ValueError("state_idx must be (batch, n)")
+        out = torch.empty(B, dtype=torch.float64, device=xd.device)
+        parts = torch.empty((B, 2), dtype=torch.float64, device=xd.device) if return_parts else None
+        jac = torch.empty((B, 2 * n, 2 * n), dtype=torch.float32, device=xd.device) if return_jac else None
+        ws = self.workspace(B, n)
+        check(lib.cgb_logp_f64io(_stream(), _ptr(xd), _ptr(sd), _ptr(self.ktable_dev()), self.M, self.twist, _ptr(pd),
+                                 B, n, self.L, _ptr(out), _ptr(parts), _ptr(jac), _ptr(ws), ws.numel()),
+              "cgb_logp_f64io")
+        res = [out] + ([parts] if return_parts else []) + ([jac] if return_jac else [])
+        if was_np:
+            res = [r.cpu().numpy() for r in res]
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def bind(self, params, state_idx):
+        """The closure `lambda x: logp(x, params_flow, state_indices)` of src/VMC.py:23, in a form the fused
+        sweep kernel can consume."""
+        return BoundLogp(self, params, state_idx)
+
+
+class BoundLogp:
+    def __init__(self, logp, params, state_idx):
+        self.logp = logp
+        self.params, _ = _to_dev(pack_params(params), torch.float64)
+        self.state_idx, _ = _to_dev(state_idx, torch.int32)
+
+    def __call__(self, x):
+        return self.logp(x, self.params, self.state_idx)
+
+
+def make_logp(sp_indices, L, depth=2, spsize=16, tpsize=16):
+    """Replaces make_logp(make_logpsi(flow, sp_indices, L)) (src/logpsi.py:7,174; main.py:162-164) for
+    flow = FermiNet(depth=2, spsize=16, tpsize=16, L) in 2D.  sp_indices = sp_indices_twist (main.py:90)."""
+    if (depth, spsize, tpsize) != (2, 16, 16):
+        raise NotImplementedError("kernels are built for depth=2, spsize=tpsize=16 (every BASELINE config)")
+    return Logp(sp_indices, L)
+
+
+# ----------------------------------------------------------------------------------------------------
+# mcmc
+# ----------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class ExplicitNoise:
+    """Parity-mode `key`: the proposal noise and acceptance uniforms that jax.random.normal/uniform would have
+    produced (src/MCMC.py:26,29).  noise (mc_steps, batch, n, 2) ~ N(0,1); uniforms (mc_steps, batch) in [0,1)."""
+    noise: object
+    uniforms: object
+
+
+def _seed_of(key):
+    if isinstance(key, (int, np.integer)):
+        return int(key) & 0xFFFFFFFFFFFFFFFF
+    k = np.asarray(key.cpu() if isinstance(key, torch.Tensor) else key).astype(np.uint64).reshape(-1)
+    if k.size != 2:
+        raise ValueError("key must be an int seed, a (2,) uint32 PRNG key, or ExplicitNoise")
+    return int((k[0] << np.uint64(32)) | k[1])
+
+
+def mcmc(logp_fn, x_init, key, mc_steps, mc_stddev=0.02, wrap_L=None, return_trace=False):
+    """Metropolis sweep with the reference's signature (src/MCMC.py:7).
+
+    logp_fn : a BoundLogp (`logp.bind(params_flow, state_indices)`); arbitrary Python callables are not supported.
+    key     : int / (2,) uint32 key -> in-kernel Philox stream (throughput mode); ExplicitNoise -> parity mode.
+    Returns (x, accept_rate) — accept_rate is this process's mean (MCMC.py:38); the cross-device pmean of
+    MCMC.py:39 is done by sample_x.  x is updated IN PLACE when x_init is a CUDA float64 tensor (donated buffer,
+    src/VMC.py:11).  wrap_L applies src/VMC.py:24 inside the kernel.  return_trace adds a dict with per-step
+    accept flags, proposal log p, final log p and per-walker accept counts."""
+    if not isinstance(logp_fn, BoundLogp):
+        raise TypeError("mcmc needs logp.bind(params_flow, state_indices); generic callables have no kernel")
+    lg = logp_fn.logp
+    xd, was_np = _to_dev(x_init, torch.float64)
+    B, n = int(xd.shape[0]), int(xd.shape[1])
+    S = int(mc_steps)
+    if tuple(logp_fn.state_idx.shape) != (B, n):
+        raise ValueError("state_indices bound to logp_fn must be (batch, n)")
+    noise = unif = None
+    seed = 0
+    if isinstance(key, ExplicitNoise):
+        noise, _ = _to_dev(key.noise, torch.float64)
+        unif, _ = _to_dev(key.uniforms, torch.float64)
+        if tuple(noise.shape) != (S, B, n, 2) or tuple(unif.shape) != (S, B):
+            raise ValueError("ExplicitNoise shapes must be (mc_steps,batch,n,2) and (mc_steps,batch)")
+    else:
+        seed = _seed_of(key)
+    dev = xd.device
+    out_logp = torch.empty(B, dtype=torch.float64, device=dev)
+    nacc = torch.empty(B, dtype=torch.int32, device=dev)
+    acc_tr = torch.empty((S, B), dtype=torch.uint8, device=dev) if return_trace else None
+    lp_tr = torch.empty((S + 1, B), dtype=torch.float64, device=dev) if return_trace else None
+    ws = lg.workspace(B, n)
+    check(lib.cgb_mcmc_sweep_f64io(_stream(), _ptr(xd), _ptr(logp_fn.state_idx), _ptr(lg.ktable_dev()), lg.M, lg.twist,
+                                   _ptr(logp_fn.params), _ptr(noise), _ptr(unif), seed, S, float(mc_stddev), lg.L,
+                                   B, n, 0 if wrap_L is None else 1, _ptr(out_logp), _ptr(nacc), _ptr(acc_tr),
+                                   _ptr(lp_tr), _ptr(ws), ws.numel()), "cgb_mcmc_sweep_f64io")
+    if wrap_L is not None and abs(float(wrap_L) - lg.L) > 1e-12 * lg.L:
+        raise ValueError("wrap_L must equal the box length the logp was built with")
+    accept_rate = nacc.sum(dtype=torch.float64) / (S * B)
+    x_out = xd.cpu().numpy() if was_np else xd
+    if was_np:
+        accept_rate = float(accept_rate)
+    if return_trace:
+        tr = dict(accept=acc_tr, logp_prop=lp_tr, logp=out_logp, naccept=nacc)
+        if was_np:
+            tr = {k: v.cpu().numpy() for k, v in tr.items()}
+        return x_out, accept_rate, tr
+    return x_out, accept_rate
+
+
+def _all_reduce_sum(vec):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return vec
+
+
+def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
+    """One sampling step of src/VMC.py:8-25 for THIS process's shard of walkers (one process per GPU replaces
+    jax.pmap): the sweep (VMC.py:23), the wrap into [0,L) (VMC.py:24) and the cross-device mean of the accept
+    rate (MCMC.py:39) as one all-reduce over the default process group (NCCL on GPUs).  The VAN draw of
+    VMC.py:22 stays with the caller, which passes `state_indices`.  Returns (key', x, accept_rate) where key'
+    is the advanced integer key."""
+    seed = _seed_of(key) if not isinstance(key, ExplicitNoise) else None
+    x, acc = mcmc(logp.bind(params_flow, state_indices), x, key, mc_steps, mc_stddev, wrap_L=L)
+    acc_t = acc if isinstance(acc, torch.Tensor) else torch.tensor(acc, dtype=torch.float64, device=_dev())
+    vec = torch.stack([acc_t, torch.ones((), dtype=torch.float64, device=acc_t.device)])
+    vec = _all_reduce_sum(vec)
+    rate = vec[0] / vec[1]                     # equal shards: mean of per-device means == global mean
+    new_key = key if seed is None else (seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+    return new_key, x, (rate if isinstance(acc, torch.Tensor) else float(rate))
+
+
+# ----------------------------------------------------------------------------------------------------
+# Ewald
+# ----------------------------------------------------------------------------------------------------
+_EWALD_CACHE = {}
+
+
+def ewald_tables(G, kappa):
+    """Fold (G, kappa) into the merged reciprocal item table (cgb_ewald_prepare_host); cached per device."""
+    Gh = np.ascontiguousarray(np.asarray(G.cpu() if isinstance(G, torch.Tensor) else G, dtype=np.int64))
+    if Gh.ndim != 2 or Gh.shape[1] != 2:
+        raise NotImplementedError("only dim=2 is supported (G must be (nG, 2))")
+    key = (Gh.tobytes(), float(kappa), torch.cuda.current_device())
+    if key not in _EWALD_CACHE:
+        items = np.empty((Gh.shape[0], 4), dtype=np.float32)
+        n_items, gmax = ctypes.c_int(), ctypes.c_int()
+        check(lib.cgb_ewald_prepare_host(Gh.ctypes.data_as(ctypes.c_void_p), Gh.shape[0], float(kappa),
+                                         items.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n_items),
+                                         ctypes.byref(gmax)), "cgb_ewald_prepare_host")
+        dev_items = torch.as_tensor(items[:n_items.value].copy()).to(_dev())
+        _EWALD_CACHE[key] = (dev_items, n_items.value, gmax.value)
+    return _EWALD_CACHE[key]
+
+
+def potential_energy(x, kappa, G, L, rs):
+    """src/potential.py:69-77 — Ewald energy (coordinate-dependent part) of a batch x (batch, n, 2) -> (batch,).
+    The caller adds Vconst = n*rs/L*Madelung (src/VMC.py:40, main.py:171)."""
+    xd, was_np = _to_dev(x, torch.float64)
+    if xd.ndim != 3 or xd.shape[2] != 2:
+        raise NotImplementedError("only dim=2 is supported (x must be (batch, n, 2))")
+    items, n_items, gmax = ewald_tables(G, kappa)
+    B, n = int(xd.shape[0]), int(xd.shape[1])
+    out = torch.empty(B, dtype=torch.float64, device=xd.device)
+    check(lib.cgb_ewald_f64io(_stream(), _ptr(xd), B, n, float(L), float(rs), float(kappa), _ptr(items), n_items, gmax,
+                              _ptr(out)), "cgb_ewald_f64io")
+    return out.cpu().numpy() if was_np else out
+
+
+def potential_stats(V):
+    """The V_mean / V2_mean entries of the pmean at src/VMC.py:46-53, as one all-reduce of [sum V, sum V^2, count]."""
+    Vd, was_np = _to_dev(V, torch.float64)
+    vec = torch.stack([Vd.sum(), (Vd * Vd).sum(), torch.tensor(float(Vd.numel()), dtype=torch.float64, device=Vd.device)])
+    vec = _all_reduce_sum(vec)
+    mean, mean2 = vec[0] / vec[2], vec[1] / vec[2]
+    return (float(mean), float(mean2)) if was_np else (mean, mean2)
+
+
+# ----------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Config:
+    """Names and defaults of the reference's flags that shape the hot path (main.py:17-43)."""
+    n: int = 13
+    dim: int = 2
+    rs: float = 10.0
+    Theta: float = 0.15
+    Emax: int = 25
+    twist: tuple = (0.25, 0.25)
+    depth: int = 2
+    spsize: int = 16
+    tpsize: int = 16
+    Gmax: int = 15
+    kappa: int = 10
+    mc_therm: int = 10
+    mc_steps: int = 50
+    mc_stddev: float = 0.1
+    batch: int = 2048
+
+    @property
+    def L(self):
+        return float(np.sqrt(np.pi * self.n))      # main.py:67
+
+
+def microbench(kind, blocks, iters):
+    """FFMA (0) / MUFU.EX2 (1) / DFMA (2) saturating micro-kernel; returns seconds (CUDA events)."""
+    out = torch.zeros(1, dtype=torch.float32, device=_dev())
+    check(lib.cgb_microbench(_stream(), kind, blocks, 64, _ptr(out)), "cgb_microbench")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib.cgb_microbench(_stream(), kind, blocks, iters, _ptr(out)), "cgb_microbench")
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3

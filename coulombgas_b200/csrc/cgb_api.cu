@@ -1,0 +1,135 @@
+// C ABI of libcgb200.so (include/cgb200.h): argument checking, host-side table preparation, launches.
+#include <math.h>
+#include <map>
+#include <utility>
+#include "cgb_internal.h"
+
+using namespace cgb;
+
+extern "C" {
+
+int cgb_abi_version(void) { return CGB_ABI_VERSION; }
+
+const char* cgb_error_string(int code) {
+    switch (code) {
+        case CGB_OK: return "ok";
+        case CGB_E_BADARG: return "bad argument";
+        case CGB_E_UNSUPPORTED: return "unsupported shape or table";
+        case CGB_E_WORKSPACE: return "workspace missing or too small";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int cgb_ktable_twist_host(const double* kt, int M, double twist_out[2]) {
+    if (!kt || M <= 0 || !twist_out) return CGB_E_BADARG;
+    const double t0 = kt[0] - rint(kt[0]), t1 = kt[1] - rint(kt[1]);
+    for (int j = 0; j < M; ++j) {
+        const double a = kt[2 * j] - t0, b = kt[2 * j + 1] - t1;
+        if (fabs(a - rint(a)) > 1e-9 || fabs(b - rint(b)) > 1e-9) return CGB_E_UNSUPPORTED;
+        if (fabs(rint(a)) > 4096 || fabs(rint(b)) > 4096) return CGB_E_UNSUPPORTED;
+    }
+    twist_out[0] = t0;
+    twist_out[1] = t1;
+    return CGB_OK;
+}
+
+int cgb_ewald_prepare_host(const int64_t* G, int nG, double kappa, float* items_out, int* n_items, int* gmax) {
+    if (!G || nG <= 0 || !items_out || !n_items || !gmax || !(kappa > 0)) return CGB_E_BADARG;
+    std::map<std::pair<int, int>, std::pair<double, double>> acc;   // (gx>=0, gy>=0) -> (w_plus, w_minus)
+    int gm = 0;
+    const double pi = 3.14159265358979323846;
+    for (int t = 0; t < nG; ++t) {
+        long gx = (long)G[2 * t], gy = (long)G[2 * t + 1];
+        if (gx == 0 && gy == 0) return CGB_E_BADARG;                 // kpoints() excludes G = 0
+        if (labs(gx) > 255 || labs(gy) > 255) return CGB_E_UNSUPPORTED;
+        const double gn = sqrt((double)(gx * gx + gy * gy));
+        const double w = erfc(pi * gn / kappa) / gn;                 // g_G, src/potential.py:58 (dim 2)
+        if (gx < 0 || (gx == 0 && gy < 0)) { gx = -gx; gy = -gy; }   // cos is even in G
+        auto& slot = acc[{(int)gx, (int)labs(gy)}];
+        if (gy >= 0) slot.first += w; else slot.second += w;
+        if (gx > gm) gm = (int)gx;
+        if (labs(gy) > gm) gm = (int)labs(gy);
+    }
+    int k = 0;
+    for (const auto& kv : acc) {
+        items_out[4 * k + 0] = (float)kv.first.first;
+        items_out[4 * k + 1] = (float)kv.first.second;
+        items_out[4 * k + 2] = (float)kv.second.first;
+        items_out[4 * k + 3] = (float)kv.second.second;
+        ++k;
+    }
+    *n_items = k;
+    *gmax = gm;
+    return CGB_OK;
+}
+
+static size_t wpack_bytes() { return ((sizeof(float) * W_TOTAL) + 255) & ~size_t(255); }
+
+int cgb_logp_workspace_bytes(int B, int n, size_t* bytes) {
+    if (!bytes || B < 0) return CGB_E_BADARG;
+    if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
+    *bytes = wpack_bytes();
+    return CGB_OK;
+}
+int cgb_mcmc_workspace_bytes(int B, int n, size_t* bytes) { return cgb_logp_workspace_bytes(B, n, bytes); }
+
+static int run_sweep(void* stream, const double* x, double* x_out, const int32_t* state_idx, const double* ktable,
+                     int M, const double twist[2], const double* params, const double* noise, const double* uniforms,
+                     uint64_t seed, int mc_steps, double sigma, double L, int B, int n, int wrap, double* out_logp,
+                     int32_t* out_naccept, uint8_t* acc_trace, double* logp_trace, double* out_parts, float* out_jac,
+                     void* workspace, size_t workspace_bytes) {
+    if (!x || !state_idx || !ktable || !twist || !params || B < 0 || M <= 0 || !(L > 0) || mc_steps < 0)
+        return CGB_E_BADARG;
+    if ((noise == nullptr) != (uniforms == nullptr)) return CGB_E_BADARG;
+    if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
+    if (!workspace || workspace_bytes < wpack_bytes() || ((uintptr_t)workspace & 15)) return CGB_E_WORKSPACE;
+    if (B == 0) return CGB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_prep_params(params, (float*)workspace, st);
+    if (rc) return rc;
+    SweepParams p;
+    p.x = x; p.x_out = x_out; p.state_idx = state_idx; p.ktable = ktable; p.M = M;
+    p.tw0 = twist[0]; p.tw1 = twist[1]; p.wpack = (const float*)workspace;
+    p.noise = noise; p.uniforms = uniforms; p.seed = seed; p.mc_steps = mc_steps; p.sigma = sigma; p.L = L;
+    p.B = B; p.n = n; p.wrap = wrap; p.out_logp = out_logp; p.out_naccept = out_naccept;
+    p.out_acc_trace = acc_trace; p.out_logp_trace = logp_trace; p.out_parts = out_parts; p.out_jac = out_jac;
+    return launch_sweep(p, st);
+}
+
+int cgb_logp_f64io(void* stream, const double* x, const int32_t* state_idx, const double* ktable, int M,
+                   const double twist[2], const double* params, int B, int n, double L, double* out_logp,
+                   double* out_parts, float* out_jac, void* workspace, size_t workspace_bytes) {
+    if (!out_logp) return CGB_E_BADARG;
+    return run_sweep(stream, x, nullptr, state_idx, ktable, M, twist, params, nullptr, nullptr, 0, 0, 0.0, L, B, n, 0,
+                     out_logp, nullptr, nullptr, nullptr, out_parts, out_jac, workspace, workspace_bytes);
+}
+
+int cgb_mcmc_sweep_f64io(void* stream, double* x_inout, const int32_t* state_idx, const double* ktable, int M,
+                         const double twist[2], const double* params, const double* noise, const double* uniforms,
+                         uint64_t seed, int mc_steps, double mc_stddev, double L, int B, int n, int wrap,
+                         double* out_logp, int32_t* out_naccept, uint8_t* out_accept_trace, double* out_logp_trace,
+                         void* workspace, size_t workspace_bytes) {
+    if (mc_steps < 1) return CGB_E_BADARG;
+    return run_sweep(stream, x_inout, x_inout, state_idx, ktable, M, twist, params, noise, uniforms, seed, mc_steps,
+                     mc_stddev, L, B, n, wrap, out_logp, out_naccept, out_accept_trace, out_logp_trace, nullptr,
+                     nullptr, workspace, workspace_bytes);
+}
+
+int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, double rs, double kappa,
+                    const float* items, int n_items, int gmax, double* out_V) {
+    if (!x || !items || !out_V || B < 0 || n_items <= 0 || !(L > 0) || !(kappa > 0)) return CGB_E_BADARG;
+    if (n < 2 || n > 128 || gmax < 1 || gmax > 255) return CGB_E_UNSUPPORTED;
+    if (((uintptr_t)items & 15)) return CGB_E_BADARG;
+    if (B == 0) return CGB_OK;
+    EwaldParams p;
+    p.x = x; p.B = B; p.n = n; p.L = L; p.rs = rs; p.kappa = kappa;
+    p.items = (const float4*)items; p.n_items = n_items; p.gmax = gmax; p.out = out_V;
+    return launch_ewald(p, (cudaStream_t)stream);
+}
+
+int cgb_microbench(void* stream, int kind, int blocks, int iters, float* out) {
+    if (kind < 0 || kind > 2 || blocks <= 0 || iters <= 0 || !out) return CGB_E_BADARG;
+    return launch_microbench(kind, blocks, iters, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Internal declarations shared by the translation units of libcgb200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/cgb200.h"
+
+namespace cgb {
+
+// FP32 weight pack produced by prep_params_kernel (floats)
+enum : int {
+    W_WT = 0,      // Wt*log2e   [5][16]   two-particle layer       (src/flow.py:46)
+    W_BT = 80,     // bt*log2e   [16]
+    W_W0C = 96,    // W0[4:9]    [5][16]   rows of W0 that see mean_j t0_ij (flow.py:34-36)
+    W_B0 = 176,    // b0         [16]
+    W_W1A = 192,   // W1[0:16]   [16][16]  acts on h_i
+    W_W1B = 448,   // W1[16:32]  [16][16]  acts on mean_k h_k
+    W_W1C = 704,   // W1[32:48]  [16][16]  acts on mean_j t_ij
+    W_B1 = 960,    // b1         [16]
+    W_WF = 976,    // Wf         [16][2]
+    W_TOTAL = 1008
+};
+
+struct SweepParams {
+    const double* x;          // (B,n,2) initial walkers
+    double* x_out;            // (B,n,2) final walkers (may alias x); unused when mc_steps == 0
+    const int32_t* state_idx; // (B,n)
+    const double* ktable;     // (M,2)
+    int M;
+    double tw0, tw1;
+    const float* wpack;       // W_TOTAL floats
+    const double* noise;      // (S,B,n,2) or null
+    const double* uniforms;   // (S,B) or null
+    uint64_t seed;
+    int mc_steps;
+    double sigma;
+    double L;
+    int B, n, wrap;
+    double* out_logp;         // (B)
+    int32_t* out_naccept;     // (B) or null
+    uint8_t* out_acc_trace;   // (S,B) or null
+    double* out_logp_trace;   // (S+1,B) or null
+    double* out_parts;        // (B,2) or null
+    float* out_jac;           // (B,2n,2n) or null
+};
+
+inline int sweep_num_warps(int n) { int w = (n + 7) / 8; return w < 2 ? 2 : w; }
+size_t sweep_smem_bytes(int n);
+int launch_sweep(const SweepParams& p, cudaStream_t st);
+int launch_prep_params(const double* params, float* wpack, cudaStream_t st);
+
+struct EwaldParams {
+    const double* x; int B, n; double L, rs, kappa;
+    const float4* items; int n_items, gmax;
+    double* out;
+};
+int launch_ewald(const EwaldParams& p, cudaStream_t st);
+int launch_microbench(int kind, int blocks, int iters, float* out, cudaStream_t st);
+
+}  // namespace cgb

@@ -1,0 +1,695 @@
+// Fused Metropolis sweep / batched log p kernel for sm_100a.
+//
+// One CTA per walker, persistent over all mc_steps of the sweep (src/MCMC.py:22-40): the walker's
+// coordinates, log p and RNG state never leave the SM between proposals.  For every proposal the CTA
+// evaluates  log p = 2 log|det D| + log|det J|  (src/logpsi.py:22-31,179):
+//   flow forward (src/flow.py:39-55) -> Slater matrix (src/slater.py:14-17) -> complex LU, and the
+//   analytic Jacobian of the flow (replacing jax.jacfwd, src/logpsi.py:27-28) -> real LU.
+//
+// Thread layout: 4 lanes per particle row ("row i, lane-in-row q"), 8 rows per warp, NW = ceil(n/8) warps.
+// In the two O(n^2) pair passes lane q of row i handles partners j = q, q+4, ...; row sums are 2-stage
+// shuffle butterflies inside the 4-lane group, so no cross-warp reduction buffers are needed.
+// Weights live in shared memory (broadcast LDS.128); per-row contractions Q_i, R_i in registers.
+// LU: one thread per matrix row, rows in shared memory (odd pitch -> conflict-free), pivot search by a
+// single REDUX (integer max of |a| bits with the row id in the low bits) + one named barrier per step;
+// the real 2n x 2n (Jacobian) and complex n x n (Slater) factorisations run concurrently on disjoint warps.
+#include "cgb_common.cuh"
+#include "cgb_internal.h"
+
+namespace cgb {
+
+// ---------------------------------------------------------------------------------------------------
+// parameter packing: float64 haiku-order vector -> FP32 kernel layout (Wt, bt pre-scaled by log2 e)
+// ---------------------------------------------------------------------------------------------------
+__global__ void prep_params_kernel(const double* __restrict__ p, float* __restrict__ w) {
+    // source offsets in the flat 1074 vector (include/cgb200.h)
+    const int S_WT = 0, S_BT = 80, S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
+    for (int t = threadIdx.x; t < W_TOTAL; t += blockDim.x) {
+        float v;
+        if (t < W_BT) v = (float)(p[S_WT + t] * 1.4426950408889634);
+        else if (t < W_W0C) v = (float)(p[S_BT + (t - W_BT)] * 1.4426950408889634);
+        else if (t < W_B0) v = (float)p[S_W0 + 4 * 16 + (t - W_W0C)];   // rows 4..8 of W0 (s0 == 0, flow.py:16-18)
+        else if (t < W_W1A) v = (float)p[S_B0 + (t - W_B0)];
+        else if (t < W_B1) v = (float)p[S_W1 + (t - W_W1A)];            // W1a | W1b | W1c contiguous
+        else if (t < W_WF) v = (float)p[S_B1 + (t - W_B1)];
+        else v = (float)p[S_WF + (t - W_WF)];                           // bf dropped: common shift of z
+        w[t] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct Smem {
+    float* wts;      // W_TOTAL
+    double* xs;      // 2n   current walker
+    double* xp;      // 2n   proposal
+    float4* pos;     // n8   (cos, sin) of half angles pi*u for x and y
+    float4* wpar;    // n8   (uh_x, ul_x, uh_y, ul_y) reduced coordinates, hi/lo split
+    float2* kint;    // n8   integer part of the occupied k rows
+    float2* dz;      // n8   backflow displacement (s_i Wf), common mode still included
+    float* sig0;     // n8*16
+    float* hbuf;     // n8*20
+    float* hbar;     // 16
+    float* Rbuf;     // n8*36  (aliases D)
+    float* Tbuf;     // n8*36
+    float* Hbuf;     // n8*36
+    float* J;        // 2n * pitchJ
+    float2* D;       // n * pitchD (aliases Rbuf/Tbuf)
+    unsigned* redJ;  // 2*8
+    unsigned* redD;  // 2*8
+    double* lsum;    // 16
+    int* flag;       // 4
+    int pitchJ, pitchD;
+};
+
+__host__ __device__ inline size_t smem_carve(int n, int n8, Smem* s, unsigned char* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    const int pitchJ = 2 * n + 1, pitchD = n | 1;
+    const size_t o_xs = take(sizeof(double) * 2 * n), o_xp = take(sizeof(double) * 2 * n);
+    const size_t o_ls = take(sizeof(double) * 16);
+    const size_t o_w = take(sizeof(float) * W_TOTAL);
+    const size_t o_pos = take(sizeof(float4) * n8), o_wp = take(sizeof(float4) * n8);
+    const size_t o_k = take(sizeof(float2) * n8), o_dz = take(sizeof(float2) * n8);
+    const size_t o_s0 = take(sizeof(float) * n8 * 16), o_h = take(sizeof(float) * n8 * 20);
+    const size_t o_hb = take(sizeof(float) * 16);
+    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(float2) * n * pitchD;
+    const size_t o_rt = take(rt > dd ? rt : dd);
+    const size_t o_H = take(sizeof(float) * n8 * 36);
+    const size_t o_J = take(sizeof(float) * 2 * n * pitchJ);
+    const size_t o_rj = take(sizeof(unsigned) * 16), o_rd = take(sizeof(unsigned) * 16);
+    const size_t o_f = take(sizeof(int) * 4);
+    if (s) {
+        s->xs = (double*)(base + o_xs); s->xp = (double*)(base + o_xp); s->lsum = (double*)(base + o_ls);
+        s->wts = (float*)(base + o_w); s->pos = (float4*)(base + o_pos); s->wpar = (float4*)(base + o_wp);
+        s->kint = (float2*)(base + o_k); s->dz = (float2*)(base + o_dz);
+        s->sig0 = (float*)(base + o_s0); s->hbuf = (float*)(base + o_h); s->hbar = (float*)(base + o_hb);
+        s->Rbuf = (float*)(base + o_rt); s->Tbuf = s->Rbuf + n8 * 36; s->D = (float2*)(base + o_rt);
+        s->Hbuf = (float*)(base + o_H); s->J = (float*)(base + o_J);
+        s->redJ = (unsigned*)(base + o_rj); s->redD = (unsigned*)(base + o_rd); s->flag = (int*)(base + o_f);
+        s->pitchJ = pitchJ; s->pitchD = pitchD;
+    }
+    return off;
+}
+
+size_t sweep_smem_bytes(int n) { return smem_carve(n, 8 * sweep_num_warps(n), nullptr, nullptr); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// pair features of (row i, partner j) from the half-angle table: cos/sin of theta = 2 pi (x_i-x_j)/L and
+// d^2 = sin^2(theta_x/2) + sin^2(theta_y/2)   (src/flow.py:22-25)
+struct PairFeat { float cx, cy, sx, sy, d2; };
+__device__ __forceinline__ PairFeat pair_features(const float4 pi_, const float4 pj) {
+    const float shx = pi_.y * pj.x - pi_.x * pj.y, chx = fmaf(pi_.x, pj.x, pi_.y * pj.y);
+    const float shy = pi_.w * pj.z - pi_.z * pj.w, chy = fmaf(pi_.z, pj.z, pi_.w * pj.w);
+    PairFeat f;
+    f.cx = fmaf(-2.f * shx, shx, 1.f);
+    f.cy = fmaf(-2.f * shy, shy, 1.f);
+    f.sx = 2.f * shx * chx;
+    f.sy = 2.f * shy * chy;
+    f.d2 = fmaf(shx, shx, shy * shy);
+    return f;
+}
+
+template <int QQ>
+__device__ __forceinline__ void store_quarter(float* dst, const float (&v)[32]) {
+    // v is [c][d] (16x2); lane QQ stores channels 4QQ..4QQ+3 -> 8 floats
+    float4* d4 = reinterpret_cast<float4*>(dst + 8 * QQ);
+    d4[0] = make_float4(v[8 * QQ + 0], v[8 * QQ + 1], v[8 * QQ + 2], v[8 * QQ + 3]);
+    d4[1] = make_float4(v[8 * QQ + 4], v[8 * QQ + 5], v[8 * QQ + 6], v[8 * QQ + 7]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, (NW <= 2 ? 10 : (NW <= 4 ? 5 : 2)))
+sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid >> 2, q = tid & 3;
+    const bool rv = row < n;
+    const int i = rv ? row : n - 1;
+    constexpr int n8 = 8 * NW;
+    Smem s;
+    smem_carve(n, n8, &s, smem_raw);
+    const int N2 = 2 * n, pJ = s.pitchJ, pD = s.pitchD;
+    const int nJw = (N2 + 31) >> 5, nDw = (n + 31) >> 5;     // LU warps: J on [0,nJw), D on [nJw, nJw+nDw)
+    const float invn = 1.f / (float)n;
+    const double invL = 1.0 / p.L;
+    const float invLf = (float)invL;
+    const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
+
+    for (int t = tid; t < W_TOTAL / 4; t += NW * 32)
+        reinterpret_cast<float4*>(s.wts)[t] = reinterpret_cast<const float4*>(p.wpack)[t];
+    const float4* wt4 = reinterpret_cast<const float4*>(s.wts + W_WT);     // [f*4+cq]
+    const float4* bt4 = reinterpret_cast<const float4*>(s.wts + W_BT);
+    const float4* w0c4 = reinterpret_cast<const float4*>(s.wts + W_W0C);   // [f*4+cq]
+    const float4* b04 = reinterpret_cast<const float4*>(s.wts + W_B0);
+    const float4* w1a4 = reinterpret_cast<const float4*>(s.wts + W_W1A);   // [row*4+cq]
+    const float4* w1b4 = reinterpret_cast<const float4*>(s.wts + W_W1B);
+    const float4* w1c4 = reinterpret_cast<const float4*>(s.wts + W_W1C);
+    const float4* b14 = reinterpret_cast<const float4*>(s.wts + W_B1);
+    const float* wf = s.wts + W_WF;                                        // [e*2+a]
+
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        __syncthreads();
+        if (tid < N2) s.xs[tid] = p.x[(size_t)b * N2 + tid];
+        if (tid < n) {
+            int si = p.state_idx[(size_t)b * n + tid];
+            si = min(max(si, 0), p.M - 1);
+            s.kint[tid] = make_float2((float)rint(p.ktable[2 * si] - p.tw0), (float)rint(p.ktable[2 * si + 1] - p.tw1));
+        }
+        double logp_cur = 0.0;   // thread 0 only
+        int nacc = 0;            // thread 0 only
+
+        for (int step = 0; step <= p.mc_steps; ++step) {
+            __syncthreads();
+            // ---------------- stage 0: proposal (MCMC.py:26) and reduced coordinates ----------------
+            if (tid < N2) {
+                double xv = s.xs[tid];
+                if (step > 0) {
+                    double nz;
+                    if (p.noise) {
+                        nz = p.noise[((size_t)(step - 1) * p.B + b) * N2 + tid];
+                    } else {
+                        const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, (uint32_t)(tid >> 1), 0u),
+                                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                        const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
+                        float sn, cs;
+                        sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
+                        nz = (double)(rad * ((tid & 1) ? sn : cs));
+                    }
+                    xv += p.sigma * nz;
+                }
+                s.xp[tid] = xv;
+                double u = xv * invL;
+                u -= floor(u);                                   // features are L-periodic (flow.py:22-25)
+                const float uh = (float)u, ul = (float)(u - (double)uh);
+                float sn, cs;
+                sincospif(uh, &sn, &cs);                         // half angle pi*u
+                const float pl = kPi * ul;
+                float* pp = reinterpret_cast<float*>(s.pos) + (tid >> 1) * 4 + (tid & 1) * 2;
+                pp[0] = fmaf(-pl, sn, cs);
+                pp[1] = fmaf(pl, cs, sn);
+                float* wp = reinterpret_cast<float*>(s.wpar) + (tid >> 1) * 4 + (tid & 1) * 2;
+                wp[0] = uh;
+                wp[1] = ul;
+            }
+            __syncthreads();
+
+            const float4 pi_ = s.pos[i];
+            const int iters = (n + 3) >> 2;
+
+            // ---------------- pass 1: two-particle stream, means over partners (flow.py:34-36,46) ----
+            float m0[5], m[16];
+            {
+#pragma unroll
+                for (int f = 0; f < 5; ++f) m0[f] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) m[c] = 0.f;
+                for (int it = 0; it < iters; ++it) {
+                    const int j = q + 4 * it;
+                    if (j < n) {
+                        const PairFeat f = pair_features(pi_, s.pos[j]);
+                        const float d = sqrt_approx(f.d2);       // 0 on the diagonal (flow.py:25)
+                        m0[0] += f.cx; m0[1] += f.cy; m0[2] += f.sx; m0[3] += f.sy; m0[4] += d;
+#pragma unroll
+                        for (int cq = 0; cq < 4; ++cq) {
+                            const float4 w0 = wt4[cq], w1 = wt4[4 + cq], w2 = wt4[8 + cq], w3 = wt4[12 + cq],
+                                         w4 = wt4[16 + cq], bb = bt4[cq];
+                            const float a0 = fmaf(d, w4.x, fmaf(f.sy, w3.x, fmaf(f.sx, w2.x, fmaf(f.cy, w1.x, fmaf(f.cx, w0.x, bb.x)))));
+                            const float a1 = fmaf(d, w4.y, fmaf(f.sy, w3.y, fmaf(f.sx, w2.y, fmaf(f.cy, w1.y, fmaf(f.cx, w0.y, bb.y)))));
+                            const float a2 = fmaf(d, w4.z, fmaf(f.sy, w3.z, fmaf(f.sx, w2.z, fmaf(f.cy, w1.z, fmaf(f.cx, w0.z, bb.z)))));
+                            const float a3 = fmaf(d, w4.w, fmaf(f.sy, w3.w, fmaf(f.sx, w2.w, fmaf(f.cy, w1.w, fmaf(f.cx, w0.w, bb.w)))));
+                            m[4 * cq + 0] += softplus2(a0);
+                            m[4 * cq + 1] += softplus2(a1);
+                            m[4 * cq + 2] += softplus2(a2);
+                            m[4 * cq + 3] += softplus2(a3);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < 5; ++f) m0[f] = quad_sum(m0[f]) * invn;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) m[c] = quad_sum(m[c]) * (kLn2 * invn);
+            }
+
+            // ---------------- single-particle stream (flow.py:45,51-55) and per-row contractions ------
+            float Q[2][5];       // d z_i / d m0_i
+            float s0own[4];      // sigma0_i for channels 4q..4q+3
+            {
+                float pre[4], h4[4];
+                {
+                    const float4 bb = b04[q];
+                    pre[0] = bb.x; pre[1] = bb.y; pre[2] = bb.z; pre[3] = bb.w;
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) {
+                        const float4 w = w0c4[f * 4 + q];
+                        pre[0] = fmaf(m0[f], w.x, pre[0]); pre[1] = fmaf(m0[f], w.y, pre[1]);
+                        pre[2] = fmaf(m0[f], w.z, pre[2]); pre[3] = fmaf(m0[f], w.w, pre[3]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) softplus_sigmoid(pre[k], h4[k], s0own[k]);
+                }
+                if (rv) {
+                    *reinterpret_cast<float4*>(s.sig0 + row * 16 + 4 * q) = make_float4(s0own[0], s0own[1], s0own[2], s0own[3]);
+                    *reinterpret_cast<float4*>(s.hbuf + row * 20 + 4 * q) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                }
+                __syncthreads();
+                if (tid < 16) {
+                    float acc = 0.f;
+                    for (int r = 0; r < n; ++r) acc += s.hbuf[r * 20 + tid];
+                    s.hbar[tid] = acc * invn;
+                }
+                __syncthreads();
+                float g[4];
+                {
+                    const float4 bb = b14[q];
+                    g[0] = bb.x; g[1] = bb.y; g[2] = bb.z; g[3] = bb.w;
+                }
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const float4 hv = *reinterpret_cast<const float4*>(s.hbuf + i * 20 + 4 * e4);
+                    const float4 hb = *reinterpret_cast<const float4*>(s.hbar + 4 * e4);
+                    const float he[4] = {hv.x, hv.y, hv.z, hv.w}, hbe[4] = {hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = 4 * e4 + k;
+                        const float4 wa = w1a4[e * 4 + q], wb = w1b4[e * 4 + q], wc = w1c4[e * 4 + q];
+                        g[0] = fmaf(he[k], wa.x, fmaf(hbe[k], wb.x, fmaf(m[e], wc.x, g[0])));
+                        g[1] = fmaf(he[k], wa.y, fmaf(hbe[k], wb.y, fmaf(m[e], wc.y, g[1])));
+                        g[2] = fmaf(he[k], wa.z, fmaf(hbe[k], wb.z, fmaf(m[e], wc.z, g[2])));
+                        g[3] = fmaf(he[k], wa.w, fmaf(hbe[k], wb.w, fmaf(m[e], wc.w, g[3])));
+                    }
+                }
+                float s1own[4], dzx = 0.f, dzy = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float sp;
+                    softplus_sigmoid(g[k], sp, s1own[k]);
+                    const float sv = h4[k] + sp;                  // s_i (flow.py:52)
+                    dzx = fmaf(sv, wf[(4 * q + k) * 2 + 0], dzx);
+                    dzy = fmaf(sv, wf[(4 * q + k) * 2 + 1], dzy);
+                }
+                dzx = quad_sum(dzx);
+                dzy = quad_sum(dzy);
+                if (rv && q == 0) s.dz[row] = make_float2(dzx, dzy);
+                // WfS[e][a] = Wf[e][a] * sigma1_i[e]
+                float wfs[16][2];
+                {
+                    const int gbase = lane & ~3;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float sg = __shfl_sync(0xffffffffu, s1own[k], gbase + qq);
+                            const int e = 4 * qq + k;
+                            wfs[e][0] = wf[2 * e] * sg;
+                            wfs[e][1] = wf[2 * e + 1] * sg;
+                        }
+                    }
+                }
+                // quarter (channels c = 4q+k) of R, T, M; Q partial
+                float Qp[2][5];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) Qp[a][f] = 0.f;
+                float Rq[2][4], Tq[2][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = 4 * q + k;
+                    float r0 = 0.f, r1 = 0.f, t0 = 0.f, t1 = 0.f, mm0 = wf[2 * c], mm1 = wf[2 * c + 1];
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 wc = w1c4[c * 4 + e4], wb = w1b4[c * 4 + e4], wa = w1a4[c * 4 + e4];
+                        const float wcv[4] = {wc.x, wc.y, wc.z, wc.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w},
+                                    wav[4] = {wa.x, wa.y, wa.z, wa.w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int e = 4 * e4 + kk;
+                            r0 = fmaf(wfs[e][0], wcv[kk], r0); r1 = fmaf(wfs[e][1], wcv[kk], r1);
+                            t0 = fmaf(wfs[e][0], wbv[kk], t0); t1 = fmaf(wfs[e][1], wbv[kk], t1);
+                            mm0 = fmaf(wfs[e][0], wav[kk], mm0); mm1 = fmaf(wfs[e][1], wav[kk], mm1);
+                        }
+                    }
+                    Rq[0][k] = r0 * kLn2; Rq[1][k] = r1 * kLn2;   // ln2: the pair pass uses Wt*log2e
+                    Tq[0][k] = t0; Tq[1][k] = t1;
+                    mm0 *= s0own[k]; mm1 *= s0own[k];
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) {
+                        const float w = s.wts[W_W0C + f * 16 + c];
+                        Qp[0][f] = fmaf(mm0, w, Qp[0][f]);
+                        Qp[1][f] = fmaf(mm1, w, Qp[1][f]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) Q[a][f] = quad_sum(Qp[a][f]);
+                if (rv) {
+                    *reinterpret_cast<float4*>(s.Rbuf + row * 36 + 4 * q) = make_float4(Rq[0][0], Rq[0][1], Rq[0][2], Rq[0][3]);
+                    *reinterpret_cast<float4*>(s.Rbuf + row * 36 + 16 + 4 * q) = make_float4(Rq[1][0], Rq[1][1], Rq[1][2], Rq[1][3]);
+                    *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 4 * q) = make_float4(Tq[0][0], Tq[0][1], Tq[0][2], Tq[0][3]);
+                    *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 16 + 4 * q) = make_float4(Tq[1][0], Tq[1][1], Tq[1][2], Tq[1][3]);
+                }
+                __syncwarp();
+            }
+
+            // ---------------- pass 2: local Jacobian blocks and the mean-field accumulators ----------
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};      // partial row sum of the off-diagonal blocks
+            {
+                float R[2][16];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 v = *reinterpret_cast<const float4*>(s.Rbuf + i * 36 + a * 16 + 4 * c4);
+                        R[a][4 * c4 + 0] = v.x; R[a][4 * c4 + 1] = v.y; R[a][4 * c4 + 2] = v.z; R[a][4 * c4 + 3] = v.w;
+                    }
+                for (int it = 0; it < iters; ++it) {
+                    const int k = q + 4 * it;
+                    if (k < n && k != i) {
+                        const PairFeat f = pair_features(pi_, s.pos[k]);
+                        const float i4d = 0.25f * rsqrt_approx(f.d2);
+                        // E_ik = (1/n) d t0_ik / d x_k   (5x2, 6 non-zeros)
+                        const float e0x = alpha * f.sx, e2x = -alpha * f.cx, e4x = -e0x * i4d;
+                        const float e1y = alpha * f.sy, e3y = -alpha * f.cy, e4y = -e1y * i4d;
+                        const float d = f.d2 * (4.f * i4d);
+                        float j00 = fmaf(Q[0][0], e0x, fmaf(Q[0][2], e2x, Q[0][4] * e4x));
+                        float j01 = fmaf(Q[0][1], e1y, fmaf(Q[0][3], e3y, Q[0][4] * e4y));
+                        float j10 = fmaf(Q[1][0], e0x, fmaf(Q[1][2], e2x, Q[1][4] * e4x));
+                        float j11 = fmaf(Q[1][1], e1y, fmaf(Q[1][3], e3y, Q[1][4] * e4y));
+#pragma unroll
+                        for (int cq = 0; cq < 4; ++cq) {
+                            const float4 w0 = wt4[cq], w1 = wt4[4 + cq], w2 = wt4[8 + cq], w3 = wt4[12 + cq],
+                                         w4 = wt4[16 + cq], bb = bt4[cq];
+                            const float w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w},
+                                        w2v[4] = {w2.x, w2.y, w2.z, w2.w}, w3v[4] = {w3.x, w3.y, w3.z, w3.w},
+                                        w4v[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const int c = 4 * cq + kk;
+                                const float a = fmaf(d, w4v[kk], fmaf(f.sy, w3v[kk], fmaf(f.sx, w2v[kk], fmaf(f.cy, w1v[kk], fmaf(f.cx, w0v[kk], bv[kk])))));
+                                const float sg = sigmoid2(a);
+                                // F_ik[c,:] = sigma_t * Wt^T E_ik   (Wt carries log2e; R carries ln2)
+                                const float fx = sg * fmaf(w0v[kk], e0x, fmaf(w2v[kk], e2x, w4v[kk] * e4x));
+                                const float fy = sg * fmaf(w1v[kk], e1y, fmaf(w3v[kk], e3y, w4v[kk] * e4y));
+                                j00 = fmaf(R[0][c], fx, j00); j01 = fmaf(R[0][c], fy, j01);
+                                j10 = fmaf(R[1][c], fx, j10); j11 = fmaf(R[1][c], fy, j11);
+                            }
+                        }
+                        if (rv) {
+                            float* jp = s.J + (2 * row) * pJ + 2 * k;
+                            jp[0] = j00; jp[1] = j01; jp[pJ] = j10; jp[pJ + 1] = j11;
+                        }
+                        rs[0] += j00; rs[1] += j01; rs[2] += j10; rs[3] += j11;
+                    }
+                }
+            }
+            // ---------------- pass 2b: H_i = d hbar / d x_i = (1/n) [ sum_k P_k E_ki - P_i sum_k E_ik ] ----
+            {
+                float Hacc[32];                      // [c][d]: sum_k sigma0_k * W0c^T (eps . E_ik)
+#pragma unroll
+                for (int t = 0; t < 32; ++t) Hacc[t] = 0.f;
+                float sE[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sum_k E_ik : (0x,2x,4x,1y,3y,4y)
+                for (int it = 0; it < iters; ++it) {
+                    const int k = q + 4 * it;
+                    if (k < n && k != i) {
+                        const PairFeat f = pair_features(pi_, s.pos[k]);
+                        const float i4d = 0.25f * rsqrt_approx(f.d2);
+                        const float e0x = alpha * f.sx, e2x = -alpha * f.cx, e4x = -e0x * i4d;
+                        const float e1y = alpha * f.sy, e3y = -alpha * f.cy, e4y = -e1y * i4d;
+#pragma unroll
+                        for (int cq = 0; cq < 4; ++cq) {
+                            const float4 v0 = w0c4[cq], v1 = w0c4[4 + cq], v2 = w0c4[8 + cq], v3 = w0c4[12 + cq],
+                                         v4 = w0c4[16 + cq];
+                            const float v0v[4] = {v0.x, v0.y, v0.z, v0.w}, v1v[4] = {v1.x, v1.y, v1.z, v1.w},
+                                        v2v[4] = {v2.x, v2.y, v2.z, v2.w}, v3v[4] = {v3.x, v3.y, v3.z, v3.w},
+                                        v4v[4] = {v4.x, v4.y, v4.z, v4.w};
+                            const float4 sk4 = *reinterpret_cast<const float4*>(s.sig0 + k * 16 + 4 * cq);
+                            const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const int c = 4 * cq + kk;
+                                // d h_k / d x_i  needs E_ki = eps . E_ik, eps = (-,-,+,+,-)
+                                const float gx = fmaf(v2v[kk], e2x, -fmaf(v0v[kk], e0x, v4v[kk] * e4x));
+                                const float gy = fmaf(v3v[kk], e3y, -fmaf(v1v[kk], e1y, v4v[kk] * e4y));
+                                Hacc[2 * c] = fmaf(skv[kk], gx, Hacc[2 * c]);
+                                Hacc[2 * c + 1] = fmaf(skv[kk], gy, Hacc[2 * c + 1]);
+                            }
+                        }
+                        sE[0] += e0x; sE[1] += e2x; sE[2] += e4x; sE[3] += e1y; sE[4] += e3y; sE[5] += e4y;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 32; ++t) Hacc[t] = quad_sum(Hacc[t]);
+#pragma unroll
+                for (int t = 0; t < 6; ++t) sE[t] = quad_sum(sE[t]);
+                // H_i = d hbar / d x_i = (1/n) [ sum_k P_k E_ki  -  P_i sum_k E_ik ]
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float s0c = s.sig0[i * 16 + c];
+                    const float ox = fmaf(s.wts[W_W0C + c], sE[0], fmaf(s.wts[W_W0C + 32 + c], sE[1], s.wts[W_W0C + 64 + c] * sE[2]));
+                    const float oy = fmaf(s.wts[W_W0C + 16 + c], sE[3], fmaf(s.wts[W_W0C + 48 + c], sE[4], s.wts[W_W0C + 64 + c] * sE[5]));
+                    Hacc[2 * c] = (Hacc[2 * c] - s0c * ox) * invn;
+                    Hacc[2 * c + 1] = (Hacc[2 * c + 1] - s0c * oy) * invn;
+                }
+                if (rv) {
+                    float* hd = s.Hbuf + row * 36;
+                    if (q == 0) store_quarter<0>(hd, Hacc);
+                    else if (q == 1) store_quarter<1>(hd, Hacc);
+                    else if (q == 2) store_quarter<2>(hd, Hacc);
+                    else store_quarter<3>(hd, Hacc);
+                }
+            }
+            __syncthreads();
+
+            // ---------------- pass 3: mean-field coupling  J_ik += T_i H_k, then the diagonal block ----
+            {
+                float T[2][16];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 v = *reinterpret_cast<const float4*>(s.Tbuf + i * 36 + a * 16 + 4 * c4);
+                        T[a][4 * c4 + 0] = v.x; T[a][4 * c4 + 1] = v.y; T[a][4 * c4 + 2] = v.z; T[a][4 * c4 + 3] = v.w;
+                    }
+                for (int it = 0; it < iters; ++it) {
+                    const int k = q + 4 * it;
+                    if (k < n && k != i) {
+                        float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2) {
+                            const float4 hv = *reinterpret_cast<const float4*>(s.Hbuf + k * 36 + 4 * c2);   // (c,x),(c,y),(c+1,x),(c+1,y)
+                            t00 = fmaf(T[0][2 * c2], hv.x, fmaf(T[0][2 * c2 + 1], hv.z, t00));
+                            t01 = fmaf(T[0][2 * c2], hv.y, fmaf(T[0][2 * c2 + 1], hv.w, t01));
+                            t10 = fmaf(T[1][2 * c2], hv.x, fmaf(T[1][2 * c2 + 1], hv.z, t10));
+                            t11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, t11));
+                        }
+                        if (rv) {
+                            float* jp = s.J + (2 * row) * pJ + 2 * k;
+                            jp[0] += t00; jp[1] += t01; jp[pJ] += t10; jp[pJ + 1] += t11;
+                        }
+                        rs[0] += t00; rs[1] += t01; rs[2] += t10; rs[3] += t11;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) rs[t] = quad_sum(rs[t]);
+                if (rv && q == 0) {          // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
+                    float* jp = s.J + (2 * row) * pJ + 2 * row;
+                    jp[0] = 1.f - rs[0]; jp[1] = -rs[1]; jp[pJ] = -rs[2]; jp[pJ + 1] = 1.f - rs[3];
+                }
+            }
+            __syncthreads();
+            if (p.out_jac && step == 0) {
+                float* oj = p.out_jac + (size_t)b * N2 * N2;
+                for (int t = tid; t < N2 * N2; t += NW * 32) oj[t] = s.J[(t / N2) * pJ + (t % N2)];
+                __syncthreads();
+            }
+
+            // ---------------- LU phase: real 2n x 2n (warps [0,nJw)) || complex n x n (next nDw warps) --
+            if (warp < nJw) {
+                const int r = tid;
+                const bool active = r < N2;
+                float* base = s.J + (active ? r : 0) * pJ;
+                bool done = !active;
+                float mylog = 0.f;
+                float cur = active ? base[0] : 0.f;          // a[r][k] for the current k
+                for (int k = 0; k < N2; ++k) {
+                    const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
+                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
+                    unsigned gmax = s.redJ[(k & 1) * 8];
+                    for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
+                    const int pr = (int)(gmax & 0x7Fu);
+                    const float* prow = s.J + pr * pJ;
+                    const float piv = prow[k];
+                    if (r == pr) {
+                        done = true;
+                        mylog = lg2_approx(fabsf(piv));
+                    } else if (!done) {
+                        const float l = -cur * rcp_approx(piv);
+                        // 1 Newton step on the reciprocal is not needed: any l gives the same determinant
+                        // up to the rounding of this row operation; keep the approx reciprocal.
+                        for (int j = k + 1; j < N2; ++j) base[j] = fmaf(l, prow[j], base[j]);
+                        if (k + 1 < N2) cur = base[k + 1];
+                    }
+                }
+                // sum log2|pivot| over rows (one pivot per row)
+                double acc = (double)mylog;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s.lsum[warp] = acc;
+            } else if (warp < nJw + nDw) {
+                const int dw = warp - nJw;
+                const int r = tid - nJw * 32;
+                const bool active = r < n;
+                float2* base = s.D + (active ? r : 0) * pD;
+                // build row r of D_rj = exp(2 pi i m_j . w_r)  (src/slater.py:14-17; twist and the common
+                // displacement are pure row/column phases and drop out of |det|)
+                if (active) {
+                    float mx = 0.f, my = 0.f;
+                    for (int t = 0; t < n; ++t) { const float2 v = s.dz[t]; mx += v.x; my += v.y; }
+                    const float2 dzi = s.dz[r];
+                    const float4 wp = s.wpar[r];
+                    const float whx = wp.x, wlx = fmaf(dzi.x - mx * invn, invLf, wp.y);
+                    const float why = wp.z, wly = fmaf(dzi.y - my * invn, invLf, wp.w);
+                    for (int j = 0; j < n; ++j) {
+                        const float2 mk = s.kint[j];
+                        float phx = mk.x * whx, ehx = fmaf(mk.x, whx, -phx);
+                        float phy = mk.y * why, ehy = fmaf(mk.y, why, -phy);
+                        phx -= rintf(phx);
+                        phy -= rintf(phy);
+                        const float lo = fmaf(mk.x, wlx, fmaf(mk.y, wly, ehx + ehy));
+                        float sn, cs;
+                        sincospif(2.f * ((phx + phy) + lo), &sn, &cs);
+                        base[j] = make_float2(cs, sn);
+                    }
+                }
+                bool done = !active;
+                float mylog = 0.f;
+                float2 cur = active ? base[0] : make_float2(0.f, 0.f);
+                for (int k = 0; k < n; ++k) {
+                    const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur.x) + fabsf(cur.y)) & ~0x7Fu) | (unsigned)r);
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0) s.redD[(k & 1) * 8 + dw] = wmax;
+                    if (nDw > 1) named_bar_sync(2, nDw * 32); else __syncwarp();
+                    unsigned gmax = s.redD[(k & 1) * 8];
+                    for (int w = 1; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                    const int pr = (int)(gmax & 0x7Fu);
+                    const float2* prow = s.D + pr * pD;
+                    const float2 piv = prow[k];
+                    const float pn = fmaf(piv.x, piv.x, piv.y * piv.y);
+                    if (r == pr) {
+                        done = true;
+                        mylog = 0.5f * lg2_approx(pn);
+                    } else if (!done) {
+                        // l = -cur / piv
+                        const float ip = rcp_approx(pn);
+                        const float lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
+                        const float ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
+                        for (int j = k + 1; j < n; ++j) {
+                            const float2 pv = prow[j];
+                            float2 v = base[j];
+                            v.x = fmaf(lx, pv.x, fmaf(-ly, pv.y, v.x));
+                            v.y = fmaf(lx, pv.y, fmaf(ly, pv.x, v.y));
+                            base[j] = v;
+                        }
+                        if (k + 1 < n) cur = base[k + 1];
+                    }
+                }
+                double acc = (double)mylog;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s.lsum[warp] = acc;
+            }
+            __syncthreads();
+
+            // ---------------- Metropolis accept / reject (MCMC.py:28-33) ------------------------------
+            if (tid == 0) {
+                double ldJ = 0.0, ldD = 0.0;
+                for (int w = 0; w < nJw; ++w) ldJ += s.lsum[w];
+                for (int w = nJw; w < nJw + nDw; ++w) ldD += s.lsum[w];
+                const double ln2 = 0.693147180559945309417;
+                ldJ *= ln2;
+                ldD = ldD * ln2 - (double)n * log(p.L);          // D carries L^{-dim/2} per entry (slater.py:17)
+                const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179
+                int acc = 1;
+                if (step == 0) {
+                    logp_cur = lp;
+                    if (p.out_parts) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = ldJ; }
+                } else {
+                    double u;
+                    if (p.uniforms) {
+                        u = p.uniforms[(size_t)(step - 1) * p.B + b];
+                    } else {
+                        const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, 0xffffffffu, 1u),
+                                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                        u = ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
+                    }
+                    const double ratio = exp(lp - logp_cur);     // MCMC.py:28
+                    acc = (u < ratio) ? 1 : 0;                   // MCMC.py:29  (NaN -> reject)
+                    if (acc) { logp_cur = lp; ++nacc; }
+                    if (p.out_acc_trace) p.out_acc_trace[(size_t)(step - 1) * p.B + b] = (uint8_t)acc;
+                }
+                if (p.out_logp_trace) p.out_logp_trace[(size_t)step * p.B + b] = lp;
+                s.flag[0] = acc;
+            }
+            __syncthreads();
+            if (step > 0 && s.flag[0] && tid < N2) s.xs[tid] = s.xp[tid];     // MCMC.py:31
+        }   // steps
+
+        __syncthreads();
+        if (p.mc_steps > 0 && tid < N2) {
+            double xv = s.xs[tid];
+            if (p.wrap) xv -= p.L * floor(xv / p.L);             // VMC.py:24
+            p.x_out[(size_t)b * N2 + tid] = xv;
+        }
+        if (tid == 0) {
+            if (p.out_logp) p.out_logp[b] = logp_cur;
+            if (p.out_naccept) p.out_naccept[b] = nacc;
+        }
+    }
+}
+
+template <int NW>
+static int launch_nw(const SweepParams& p, cudaStream_t st) {
+    const size_t smem = sweep_smem_bytes(p.n);
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<NW>, NW * 32, smem);
+    if (occ < 1) occ = 1;
+    int grid = p.B < sms * occ ? p.B : sms * occ;
+    sweep_kernel<NW><<<grid, NW * 32, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int launch_sweep(const SweepParams& p, cudaStream_t st) {
+    switch (sweep_num_warps(p.n)) {
+        case 2: return launch_nw<2>(p, st);
+        case 3: return launch_nw<3>(p, st);
+        case 4: return launch_nw<4>(p, st);
+        case 5: return launch_nw<5>(p, st);
+        case 6: return launch_nw<6>(p, st);
+        case 7: return launch_nw<7>(p, st);
+        case 8: return launch_nw<8>(p, st);
+        default: return CGB_E_UNSUPPORTED;
+    }
+}
+
+int launch_prep_params(const double* params, float* wpack, cudaStream_t st) {
+    prep_params_kernel<<<1, 256, 0, st>>>(params, wpack);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cgb

@@ -1,0 +1,117 @@
+/*
+ * cgb200.h — C ABI of libcgb200.so: B200 (sm_100a) kernels for the forward-sampling hot path of
+ * fermiflow/CoulombGas.  Reference file:line citations are relative to the reference tree.
+ *
+ * The reference has no plugin / FFI interface: its hot path is three Python callables.
+ * Each launcher below replaces one of them and is what a jax.ffi custom call binds:
+ *
+ *   cgb_logp_f64io         <->  logp(x, params, state_idx)                 src/logpsi.py:174-181
+ *                               (= 2*Re logpsi: flow src/flow.py:39-55, Slater log-det src/slater.py:4-19,
+ *                                + 0.5*slogdet(jacfwd(flow)) src/logpsi.py:22-31)
+ *   cgb_mcmc_sweep_f64io   <->  mcmc(logp_fn, x_init, key, mc_steps, mc_stddev)   src/MCMC.py:6-40
+ *                               and the wrap x -= L*floor(x/L)                     src/VMC.py:24
+ *   cgb_ewald_f64io        <->  potential_energy(x, kappa, G, L, rs)       src/potential.py:36-77
+ *
+ * Conventions (all launchers):
+ *   - asynchronous on the caller's stream (`stream` is a cudaStream_t passed as void*), device pointers
+ *     only, no allocation, no synchronisation, no global mutable state (reentrant; one call per stream
+ *     at a time per workspace); the caller owns every buffer; workspace size comes from the *_workspace_bytes
+ *     query.
+ *   - I/O buffers are float64 (the reference runs with jax_enable_x64, main.py:2-3); internal arithmetic is
+ *     FP32 with float64 range reduction / log-det accumulation / Metropolis test.
+ *   - return 0 on success, CGB_E_* (<0) for bad arguments / unsupported shapes, or the positive
+ *     cudaError_t of a failed launch.  Nothing throws.
+ *   - supported model shape: dim = 2, depth = 2, spsize = tpsize = 16 (the shape of every BASELINE.json
+ *     config), 2 <= n <= 64, k-table rows = integer + one common twist (src/orbitals.py:46-55).
+ */
+#ifndef CGB200_H
+#define CGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGB_OK               0
+#define CGB_E_BADARG        -1   /* null pointer, non-positive size, ... */
+#define CGB_E_UNSUPPORTED   -2   /* n out of range, dim != 2, k-table not integer+twist, ... */
+#define CGB_E_WORKSPACE     -3   /* workspace missing or too small */
+
+#define CGB_NPARAMS        1074  /* flat flow parameter vector, see cgb_pack order below */
+#define CGB_MAX_N            64
+#define CGB_ABI_VERSION       1
+
+/* Flat parameter layout (float64, CGB_NPARAMS entries), haiku module names of src/flow.py:
+ *   Wt (5x16)  bt (16)   "fermi_net/~/linear_2"   two-particle layer   src/flow.py:13,46
+ *   W0 (9x16)  b0 (16)   "fermi_net/~/linear"     single-particle #0   src/flow.py:11,45
+ *   W1 (48x16) b1 (16)   "fermi_net/~/linear_1"   single-particle #1   src/flow.py:11,52
+ *   Wf (16x2)  bf (2)    "fermi_net/linear"       final                src/flow.py:54
+ * weights row-major (in, out) exactly as haiku stores `w`. */
+
+int cgb_abi_version(void);
+const char* cgb_error_string(int code);
+
+/* ---- host helpers (pure CPU, no CUDA calls) ------------------------------------------------- */
+
+/* Validate a k-table `sp_indices_twist` (M x 2, float64, host) = integer + common twist
+ * (main.py:86-90).  Writes the twist.  Returns CGB_E_UNSUPPORTED otherwise. */
+int cgb_ktable_twist_host(const double* ktable_host, int M, double twist_out[2]);
+
+/* Fold the reference's G list (nG x 2 integers, src/potential.py:7-17) and kappa into the merged
+ * reciprocal-space item table the Ewald kernel consumes: items_out[4*t + {0,1,2,3}] =
+ * {gx >= 0, gy >= 0, weight of (gx,gy)&(-gx,-gy), weight of (gx,-gy)&(-gx,gy)} as float32 bit-compatible
+ * floats, weights = g_G of src/potential.py:58 (2D).  items_out must hold 4*nG floats; *n_items <= nG.
+ * Also returns max |G| component in *gmax (table size the kernel needs). */
+int cgb_ewald_prepare_host(const int64_t* G_host, int nG, double kappa, float* items_out,
+                           int* n_items, int* gmax);
+
+/* ---- workspace queries ---------------------------------------------------------------------- */
+int cgb_logp_workspace_bytes(int B, int n, size_t* bytes);
+int cgb_mcmc_workspace_bytes(int B, int n, size_t* bytes);
+
+/* ---- logp  (src/logpsi.py:174-181) ---------------------------------------------------------- */
+/* x (B,n,2) f64; state_idx (B,n) int32 in [0,M); ktable (M,2) f64 device; twist from
+ * cgb_ktable_twist_host; params (CGB_NPARAMS) f64 device; out_logp (B) f64.
+ * Optional debug outputs (may be NULL): out_parts (B,2) f64 = {log|det D| (incl. -n log L), log|det J|};
+ * out_jac (B,2n,2n) f32 = the analytic flow Jacobian. */
+int cgb_logp_f64io(void* stream, const double* x, const int32_t* state_idx, const double* ktable, int M,
+                   const double twist[2], const double* params, int B, int n, double L,
+                   double* out_logp, double* out_parts, float* out_jac, void* workspace,
+                   size_t workspace_bytes);
+
+/* ---- Metropolis sweep  (src/MCMC.py:22-40 + src/VMC.py:24) ---------------------------------- */
+/* x_inout (B,n,2) f64 is advanced in place by mc_steps all-electron Gaussian moves (donated buffer,
+ * src/VMC.py:11).  Parity mode: noise (mc_steps,B,n,2) f64 ~ N(0,1) and uniforms (mc_steps,B) f64 in
+ * [0,1) are supplied by the caller (they replace jax.random.normal/uniform, MCMC.py:26,29).
+ * Throughput mode: noise == uniforms == NULL and the kernel draws from Philox4x32-10 keyed by `seed`.
+ * wrap != 0 applies x -= L*floor(x/L) at the end (VMC.py:24).
+ * Outputs: out_logp (B) f64 final log p per walker; out_naccept (B) int32 accepted moves per walker
+ * (accept_rate = sum / (mc_steps*B), MCMC.py:38-39 — the cross-device mean is the caller's psum);
+ * out_accept_trace (mc_steps,B) uint8 or NULL; out_logp_trace (mc_steps+1,B) f64 proposal log p
+ * (row 0 = initial) or NULL. */
+int cgb_mcmc_sweep_f64io(void* stream, double* x_inout, const int32_t* state_idx, const double* ktable,
+                         int M, const double twist[2], const double* params, const double* noise,
+                         const double* uniforms, uint64_t seed, int mc_steps, double mc_stddev, double L,
+                         int B, int n, int wrap, double* out_logp, int32_t* out_naccept,
+                         uint8_t* out_accept_trace, double* out_logp_trace, void* workspace,
+                         size_t workspace_bytes);
+
+/* ---- Ewald energy  (src/potential.py:36-77) ------------------------------------------------- */
+/* x (B,n,2) f64; items (n_items x 4 floats, device) and gmax from cgb_ewald_prepare_host;
+ * out_V (B) f64 = 2*rs/L * psi(x/L)   (caller adds Vconst, src/VMC.py:40). */
+int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, double rs, double kappa,
+                    const float* items, int n_items, int gmax, double* out_V);
+
+/* ---- roofline micro-benchmarks (bench.py only): FFMA / MUFU.EX2 saturating kernels ---------- */
+/* Runs `iters` dependent-chain iterations on `blocks` x 256 threads; writes a checksum to out (1 float).
+ * kind 0: 8 independent FFMA chains per thread (2*8*iters flop per thread);
+ * kind 1: 8 independent ex2.approx chains (8*iters MUFU ops per thread);
+ * kind 2: 8 independent DFMA chains (float64). */
+int cgb_microbench(void* stream, int kind, int blocks, int iters, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGB200_H */
