@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the forward-sampling hot path (BASELINE.json metric).
+
+One "step" = one sampling step of the reference's training loop for this rank's shard of walkers
+(main.py:334-338 -> src/VMC.py:8-25 -> src/MCMC.py): a Metropolis sweep of mc_steps=50 all-electron proposals
+(51 evaluations of log p per walker) followed by one Ewald energy evaluation of the final walkers
+(src/VMC.py:40).  Workload = BASELINE.json configs[2]: n=29, dim 2, rs=1, Emax=25 (M=81), Gmax=15 (|G|=708),
+kappa=10, batch 2048 walkers per GPU (weak scaling: every rank holds a full 2048-walker batch).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  torchrun ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+Prints ONE JSON line (rank 0).  `value` = walker-steps/s with inputs resident in HBM (device timed, CUDA events
+on the launching stream, max over ranks); `e2e` = the same through the public host-buffer API with H2D/D2H
+copies inside the timed region; `roofline` = FP32 work rate of the sweep kernel vs the FFMA peak measured by
+a saturating micro-kernel in this same process; `cpu_baseline` = the float64 restated reference algorithm
+(oracle/) timed on this box's host cores on a bounded sample.  --impl reference times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+CFG = dict(tag="n29_rs1", n=29, dim=2, rs=1.0, Emax=25, Gmax=15, kappa=10, mc_steps=50, mc_stddev=0.1, batch=2048)
+METRIC = "metropolis_walker_steps_per_sec"
+UNIT = "walker-steps/s"
+
+
+def load_inputs(B, rank=0):
+    """Synthetic inputs of the named shape: the shipped checkpoint walkers (device-0 shard, 256
+    walkers) tiled to B with seeded N(0,0.1^2) jitter; trained flow parameters; state_idx even=ground state,
+    odd=sorted random subset."""
+    from conftest import load_case
+    c = load_case(CFG["tag"])
+    rng = np.random.default_rng(42 + rank)
+    reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+    x = np.tile(c["x"], (reps, 1, 1))[:B] + 0.1 * rng.standard_normal((B, c["n"], 2))
+    x = x - c["L"] * np.floor(x / c["L"])
+    M = c["ktable"].shape[0]
+    si = np.empty((B, c["n"]), dtype=np.int32)
+    rs = np.random.default_rng(43 + rank)
+    for b in range(B):
+        si[b] = np.arange(M - c["n"], M) if b % 2 == 0 else np.sort(rs.choice(M, size=c["n"], replace=False))
+    return c, x, si
+
+
+def make_config(B, world):
+    return {"workload": "configs[2]: n=29 dim=2 rs=1.0 Theta=0.15 Emax=25 (M=81) Gmax=15 (|G|=708) kappa=10, "
+                        "batch %d walkers/GPU, mc_steps=50 (51 log p evals/walker) + 1 Ewald eval/walker per step" % B,
+            "inputs": "shipped checkpoint walkers tiled + N(0,0.1) jitter, trained flow params, in-kernel Philox",
+            "l2": "256 MiB write between timed iterations (L2 flush); working set itself is < L2",
+            "parallelism": "dp%d (walkers sharded, 2 scalar all-reduces/step)" % world}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([t.strip() for t in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(c, x, si, G, walkers, mc_steps, threads):
+    """The restated reference algorithm (oracle/: vmap'd flow + jacfwd + LAPACK slogdet, Metropolis step,
+    pairwise-cos Ewald) on `threads` host cores.  Returns (walker-steps/s, ewald evals/s, seconds)."""
+    import torch
+    from oracle import logpsi as ol, mcmc as om, potential as op
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(7)
+    xs, sis = x[:walkers], si[:walkers]
+    noise, unif = rng.standard_normal((mc_steps, walkers, c["n"], 2)), rng.random((mc_steps, walkers))
+    lp = lambda y: ol.logp_batch(y, c["params"], sis, c["ktable"], c["L"], chunk=32)
+    ol.logp_batch(xs[:2], c["params"], sis[:2], c["ktable"], c["L"])     # warm-up (torch.func first-call overhead)
+    t0 = time.perf_counter()
+    xo, acc = om.mcmc(lp, xs, noise, unif, mc_steps, CFG["mc_stddev"])
+    t1 = time.perf_counter()
+    op.potential_energy(om.wrap(xo, c["L"]), c["kappa"], G, c["L"], c["rs"])
+    t2 = time.perf_counter()
+    # walker-steps/s for a full sampling step: sweep of mc_steps proposals (+1 initial eval) + Ewald
+    per_walker = (t1 - t0) / walkers * (CFG["mc_steps"] + 1) / (mc_steps + 1) + (t2 - t1) / walkers
+    return CFG["mc_steps"] / per_walker, walkers / (t2 - t1), t2 - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  JAX/jaxlib/haiku are not installable
+    in this image (no wheels, no network), so this is the float64 restatement of the reference
+    algorithm as written (oracle/), all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    c, x, si = load_inputs(256)
+    from oracle import tables
+    G = tables.kpoints(2, CFG["Gmax"])
+    walkers, sub_steps = 32, 2
+    vals, secs = [], []
+    for it in range(args.warmup + args.steps):
+        v, ew, s = cpu_reference_rate(c, x, si, G, walkers, sub_steps, threads)
+        if it >= args.warmup:
+            vals.append(v); secs.append(s)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": make_config(args.batch, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d walkers x (%d proposals + 1 initial log p) + Ewald per step, "
+                                       "scaled to the 50-proposal sweep; torch-f64 vmap+jacfwd+LAPACK"
+                                       % (walkers, sub_steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["batch"], help="walkers per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import coulombgas_b200 as cg
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, n = args.batch, CFG["mc_steps"], CFG["n"]
+    c, x_host, si_host = load_inputs(B, rank)
+    G = cg.kpoints(2, CFG["Gmax"])
+    Vconst = n * c["rs"] / c["L"] * cg.madelung(2, CFG["kappa"], G)
+    logp = cg.make_logp(c["ktable"], c["L"])
+    params = torch.as_tensor(cg.pack_params(c["params"]), device=dev)
+    si = torch.as_tensor(si_host, device=dev)
+    x0 = torch.as_tensor(x_host, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step(x, key):
+        key, x, acc = cg.sample_x(key, si, logp, x, params, S, CFG["mc_stddev"], c["L"])     # sweep + wrap + psum
+        V = cg.potential_energy(x, CFG["kappa"], G, c["L"], c["rs"]) + Vconst                 # VMC.py:40
+        vm, v2 = cg.potential_stats(V)                                                        # VMC.py:46-53 (V entries)
+        return key, x, acc, vm, v2
+
+    key = 1000 + rank
+    x = x0.clone()
+    for _ in range(args.warmup):
+        key, x, acc, vm, v2 = step(x, key)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                      # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        key, x, acc, vm, v2 = step(x, key)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.finish()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax)
+    value = world * B * S / (ms * 1e-3)
+
+    # ---- kernel-only timings for the roofline (sweep kernel alone, Ewald kernel alone), CUDA events
+    bound = logp.bind(params, si)
+
+    def time_fn(fn, reps):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+    xk = x.clone()
+    ms_sweep = time_fn(lambda: cg.mcmc(bound, xk, 77, S, CFG["mc_stddev"], wrap_L=c["L"]), 5)
+    ms_ewald = time_fn(lambda: cg.potential_energy(xk, CFG["kappa"], G, c["L"], c["rs"]), 10)
+    blocks = 148 * 8
+    ffma = max(2 * 8 * 20000 * blocks * 256 / cg.microbench(0, blocks, 20000) for _ in range(3)) / 1e12
+    mufu = max(8 * 20000 * blocks * 256 / cg.microbench(1, blocks, 20000) for _ in range(3)) / 1e12
+    flop = cg.flops.flop_sweep(n, S) * B
+    achieved = flop / (ms_sweep * 1e-3) / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    xh = torch.as_tensor(x_host).pin_memory()
+    sih = torch.as_tensor(si_host).pin_memory()
+    xo = torch.empty_like(xh).pin_memory()
+    Vo = torch.empty(B, dtype=torch.float64).pin_memory()
+    stats = torch.empty(3, dtype=torch.float64).pin_memory()
+
+    def e2e_step(k):
+        xd = xh.to(dev, non_blocking=True)
+        sd = sih.to(dev, non_blocking=True)
+        _, xd, acc_, = cg.sample_x(5000 + k, sd, logp, xd, params, S, CFG["mc_stddev"], c["L"])
+        V = cg.potential_energy(xd, CFG["kappa"], G, c["L"], c["rs"]) + Vconst
+        vm_, v2_ = cg.potential_stats(V)
+        xo.copy_(xd, non_blocking=True)
+        Vo.copy_(V, non_blocking=True)
+        stats.copy_(torch.stack([acc_, vm_, v2_]), non_blocking=True)
+    for k in range(2):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ke = max(3, args.steps // 2)
+    a.record()
+    for k in range(ke):
+        e2e_step(10 + k)
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([a.elapsed_time(b) / ke], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * S / (float(e2e_ms) * 1e-3)
+    h2d = xh.numel() * 8 + sih.numel() * 4
+    d2h = xo.numel() * 8 + Vo.numel() * 8 + 3 * 8
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (f64 I/O, range reduction, log-det sums and Metropolis test)", "data": "synthetic",
+        "config": make_config(B, world),
+        "ewald_evals_per_sec": world * B / (ms_ewald * 1e-3),
+        "sweep_kernel_ms": ms_sweep, "ewald_kernel_ms": ms_ewald,
+        "accept_rate": float(acc), "V_mean_over_rs2": float(vm) / c["rs"] ** 2,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
+                     "traffic": None, "kernel": "sweep_kernel<4>",
+                     "note": "compute-bound path (>2000 FLOP/B): achieved = (8n^3+895n^2+1760n)*(mc_steps+1)*B algorithmic "
+                             "FLOP / CUDA-event kernel time; peak = FFMA-saturating micro-kernel measured in this run "
+                             "(MEASURED_PEAKS.json has only HBM %s GB/s and bf16); MUFU peak %.2f Top/s"
+                             % (peaks.get("hbm_gbs"), mufu)},
+        "wall_s_timed_region": t_wall,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            from oracle import tables
+            v, ew, secs = cpu_reference_rate(c, x_host, si_host, tables.kpoints(2, CFG["Gmax"]), 64, 3, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "64 walkers x (3 proposals + initial log p) + Ewald, scaled to the 50-proposal "
+                                              "sweep; restated reference algorithm (torch-f64 vmap+jacfwd+LAPACK), %.1f s" % secs,
+                                    "ewald_evals_per_sec": ew}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

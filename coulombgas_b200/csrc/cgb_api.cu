@@ -78,6 +78,7 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
                      uint64_t seed, int mc_steps, double sigma, double L, int B, int n, int wrap, double* out_logp,
                      int32_t* out_naccept, uint8_t* acc_trace, double* logp_trace, double* out_parts, float* out_jac,
                      void* workspace, size_t workspace_bytes) {
+    if (B == 0) return CGB_OK;
     if (!x || !state_idx || !ktable || !twist || !params || B < 0 || M <= 0 || !(L > 0) || mc_steps < 0)
         return CGB_E_BADARG;
     if ((noise == nullptr) != (uniforms == nullptr)) return CGB_E_BADARG;
@@ -99,7 +100,7 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
 int cgb_logp_f64io(void* stream, const double* x, const int32_t* state_idx, const double* ktable, int M,
                    const double twist[2], const double* params, int B, int n, double L, double* out_logp,
                    double* out_parts, float* out_jac, void* workspace, size_t workspace_bytes) {
-    if (!out_logp) return CGB_E_BADARG;
+    if (!out_logp && B > 0) return CGB_E_BADARG;
     return run_sweep(stream, x, nullptr, state_idx, ktable, M, twist, params, nullptr, nullptr, 0, 0, 0.0, L, B, n, 0,
                      out_logp, nullptr, nullptr, nullptr, out_parts, out_jac, workspace, workspace_bytes);
 }
@@ -117,6 +118,7 @@ int cgb_mcmc_sweep_f64io(void* stream, double* x_inout, const int32_t* state_idx
 
 int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, double rs, double kappa,
                     const float* items, int n_items, int gmax, double* out_V) {
+    if (B == 0) return CGB_OK;
     if (!x || !items || !out_V || B < 0 || n_items <= 0 || !(L > 0) || !(kappa > 0)) return CGB_E_BADARG;
     if (n < 2 || n > 128 || gmax < 1 || gmax > 255) return CGB_E_UNSUPPORTED;
     if (((uintptr_t)items & 15)) return CGB_E_BADARG;
