@@ -84,13 +84,14 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     if ((noise == nullptr) != (uniforms == nullptr)) return CGB_E_BADARG;
     if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
     if (!workspace || workspace_bytes < wpack_bytes() || ((uintptr_t)workspace & 15)) return CGB_E_WORKSPACE;
+    if ((uintptr_t)params & 15) return CGB_E_BADARG;            // float64 parameters are read as 16-byte pairs
     if (B == 0) return CGB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_prep_params(params, (float*)workspace, st);
     if (rc) return rc;
     SweepParams p;
     p.x = x; p.x_out = x_out; p.state_idx = state_idx; p.ktable = ktable; p.M = M;
-    p.tw0 = twist[0]; p.tw1 = twist[1]; p.wpack = (const float*)workspace;
+    p.tw0 = twist[0]; p.tw1 = twist[1]; p.wpack = (const float*)workspace; p.params = params;
     p.noise = noise; p.uniforms = uniforms; p.seed = seed; p.mc_steps = mc_steps; p.sigma = sigma; p.L = L;
     p.B = B; p.n = n; p.wrap = wrap; p.out_logp = out_logp; p.out_naccept = out_naccept;
     p.out_acc_trace = acc_trace; p.out_logp_trace = logp_trace; p.out_parts = out_parts; p.out_jac = out_jac;

@@ -29,6 +29,7 @@ struct SweepParams {
     int M;
     double tw0, tw1;
     const float* wpack;       // W_TOTAL floats
+    const double* params;     // the caller's flat float64 parameters (forward pass of the single-particle stream)
     const double* noise;      // (S,B,n,2) or null
     const double* uniforms;   // (S,B) or null
     uint64_t seed;

@@ -43,17 +43,17 @@ struct Smem {
     double* xs;      // 2n   current walker
     double* xp;      // 2n   proposal
     float4* pos;     // n8   (cos, sin) of half angles pi*u for x and y
-    float4* wpar;    // n8   (uh_x, ul_x, uh_y, ul_y) reduced coordinates, hi/lo split
+    double2* us;     // n8   reduced coordinates u = frac(x/L), float64
     float2* kint;    // n8   integer part of the occupied k rows
-    float2* dz;      // n8   backflow displacement (s_i Wf), common mode still included
+    double2* dz;     // n8   backflow displacement (s_i Wf) in float64, common mode still included
     float* sig0;     // n8*16
-    float* hbuf;     // n8*20
-    float* hbar;     // 16
+    double* hbuf;    // n8*18  h_i in float64
+    double* hbar;    // 16
     float* Rbuf;     // n8*36  (aliases D)
     float* Tbuf;     // n8*36
     float* Hbuf;     // n8*36
-    float* J;        // 2n * pitchJ
-    float2* D;       // n * pitchD (aliases Rbuf/Tbuf)
+    float* J;        // 2n * pitchJ   (pitchJ = 4*odd: conflict-free LDS.128 by row)
+    double2* D;      // n * pitchD complex float64 (aliases Rbuf/Tbuf)
     unsigned* redJ;  // 2*8
     unsigned* redD;  // 2*8
     double* lsum;    // 16
@@ -64,15 +64,15 @@ struct Smem {
 __host__ __device__ inline size_t smem_carve(int n, int n8, Smem* s, unsigned char* base) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-    const int pitchJ = 2 * n + 1, pitchD = n | 1;
+    const int pitchJ = 4 * (((2 * n + 3) / 4) | 1), pitchD = n | 1;
     const size_t o_xs = take(sizeof(double) * 2 * n), o_xp = take(sizeof(double) * 2 * n);
     const size_t o_ls = take(sizeof(double) * 16);
     const size_t o_w = take(sizeof(float) * W_TOTAL);
-    const size_t o_pos = take(sizeof(float4) * n8), o_wp = take(sizeof(float4) * n8);
-    const size_t o_k = take(sizeof(float2) * n8), o_dz = take(sizeof(float2) * n8);
-    const size_t o_s0 = take(sizeof(float) * n8 * 16), o_h = take(sizeof(float) * n8 * 20);
-    const size_t o_hb = take(sizeof(float) * 16);
-    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(float2) * n * pitchD;
+    const size_t o_pos = take(sizeof(float4) * n8), o_us = take(sizeof(double2) * n8);
+    const size_t o_k = take(sizeof(float2) * n8), o_dz = take(sizeof(double2) * n8);
+    const size_t o_s0 = take(sizeof(float) * n8 * 16), o_h = take(sizeof(double) * n8 * 18);
+    const size_t o_hb = take(sizeof(double) * 16);
+    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(double2) * n * pitchD;
     const size_t o_rt = take(rt > dd ? rt : dd);
     const size_t o_H = take(sizeof(float) * n8 * 36);
     const size_t o_J = take(sizeof(float) * 2 * n * pitchJ);
@@ -80,10 +80,10 @@ __host__ __device__ inline size_t smem_carve(int n, int n8, Smem* s, unsigned ch
     const size_t o_f = take(sizeof(int) * 4);
     if (s) {
         s->xs = (double*)(base + o_xs); s->xp = (double*)(base + o_xp); s->lsum = (double*)(base + o_ls);
-        s->wts = (float*)(base + o_w); s->pos = (float4*)(base + o_pos); s->wpar = (float4*)(base + o_wp);
-        s->kint = (float2*)(base + o_k); s->dz = (float2*)(base + o_dz);
-        s->sig0 = (float*)(base + o_s0); s->hbuf = (float*)(base + o_h); s->hbar = (float*)(base + o_hb);
-        s->Rbuf = (float*)(base + o_rt); s->Tbuf = s->Rbuf + n8 * 36; s->D = (float2*)(base + o_rt);
+        s->wts = (float*)(base + o_w); s->pos = (float4*)(base + o_pos); s->us = (double2*)(base + o_us);
+        s->kint = (float2*)(base + o_k); s->dz = (double2*)(base + o_dz);
+        s->sig0 = (float*)(base + o_s0); s->hbuf = (double*)(base + o_h); s->hbar = (double*)(base + o_hb);
+        s->Rbuf = (float*)(base + o_rt); s->Tbuf = s->Rbuf + n8 * 36; s->D = (double2*)(base + o_rt);
         s->Hbuf = (float*)(base + o_H); s->J = (float*)(base + o_J);
         s->redJ = (unsigned*)(base + o_rj); s->redD = (unsigned*)(base + o_rd); s->flag = (int*)(base + o_f);
         s->pitchJ = pitchJ; s->pitchD = pitchD;
@@ -101,6 +101,28 @@ __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
 }
+
+__device__ __forceinline__ double quad_sum_f64(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+// Kahan-compensated accumulation: the sums over partners feed the Slater phases, whose condition number
+// amplifies FP32 summation error past the 1e-5 budget.
+__device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
+    const float y = x - comp;
+    const float t = sum + y;
+    comp = (t - sum) - y;
+    sum = t;
+}
+// float64 softplus (forward value) + FP32 logistic sigmoid (Jacobian side) of a float64 pre-activation
+__device__ __forceinline__ void softplus_sigmoid_f64(double pre, double& sp, float& sg) {
+    const double e = exp(-fabs(pre));
+    sp = fmax(pre, 0.0) + log1p(e);
+    const float ef = (float)e, r = rcp_approx(1.f + ef);
+    sg = pre >= 0.0 ? r : ef * r;
+}
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // pair features of (row i, partner j) from the half-angle table: cos/sin of theta = 2 pi (x_i-x_j)/L and
 // d^2 = sin^2(theta_x/2) + sin^2(theta_y/2)   (src/flow.py:22-25)
@@ -141,7 +163,6 @@ sweep_kernel(const SweepParams p) {
     const int nJw = (N2 + 31) >> 5, nDw = (n + 31) >> 5;     // LU warps: J on [0,nJw), D on [nJw, nJw+nDw)
     const float invn = 1.f / (float)n;
     const double invL = 1.0 / p.L;
-    const float invLf = (float)invL;
     const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
 
     for (int t = tid; t < W_TOTAL / 4; t += NW * 32)
@@ -196,9 +217,7 @@ sweep_kernel(const SweepParams p) {
                 float* pp = reinterpret_cast<float*>(s.pos) + (tid >> 1) * 4 + (tid & 1) * 2;
                 pp[0] = fmaf(-pl, sn, cs);
                 pp[1] = fmaf(pl, cs, sn);
-                float* wp = reinterpret_cast<float*>(s.wpar) + (tid >> 1) * 4 + (tid & 1) * 2;
-                wp[0] = uh;
-                wp[1] = ul;
+                reinterpret_cast<double*>(s.us)[tid] = u;
             }
             __syncthreads();
 
@@ -206,18 +225,22 @@ sweep_kernel(const SweepParams p) {
             const int iters = (n + 3) >> 2;
 
             // ---------------- pass 1: two-particle stream, means over partners (flow.py:34-36,46) ----
-            float m0[5], m[16];
+            // FP32 terms, Kahan-compensated sums, float64 from the 4-lane butterfly onwards.
+            double m0d[5], md[16];
             {
+                float m0[5], m0c[5], m[16], mc[16];
 #pragma unroll
-                for (int f = 0; f < 5; ++f) m0[f] = 0.f;
+                for (int f = 0; f < 5; ++f) { m0[f] = 0.f; m0c[f] = 0.f; }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) m[c] = 0.f;
+                for (int c = 0; c < 16; ++c) { m[c] = 0.f; mc[c] = 0.f; }
                 for (int it = 0; it < iters; ++it) {
                     const int j = q + 4 * it;
                     if (j < n) {
                         const PairFeat f = pair_features(pi_, s.pos[j]);
                         const float d = sqrt_approx(f.d2);       // 0 on the diagonal (flow.py:25)
-                        m0[0] += f.cx; m0[1] += f.cy; m0[2] += f.sx; m0[3] += f.sy; m0[4] += d;
+                        kahan_add(m0[0], m0c[0], f.cx); kahan_add(m0[1], m0c[1], f.cy);
+                        kahan_add(m0[2], m0c[2], f.sx); kahan_add(m0[3], m0c[3], f.sy);
+                        kahan_add(m0[4], m0c[4], d);
 #pragma unroll
                         for (int cq = 0; cq < 4; ++cq) {
                             const float4 w0 = wt4[cq], w1 = wt4[4 + cq], w2 = wt4[8 + cq], w3 = wt4[12 + cq],
@@ -226,80 +249,89 @@ sweep_kernel(const SweepParams p) {
                             const float a1 = fmaf(d, w4.y, fmaf(f.sy, w3.y, fmaf(f.sx, w2.y, fmaf(f.cy, w1.y, fmaf(f.cx, w0.y, bb.y)))));
                             const float a2 = fmaf(d, w4.z, fmaf(f.sy, w3.z, fmaf(f.sx, w2.z, fmaf(f.cy, w1.z, fmaf(f.cx, w0.z, bb.z)))));
                             const float a3 = fmaf(d, w4.w, fmaf(f.sy, w3.w, fmaf(f.sx, w2.w, fmaf(f.cy, w1.w, fmaf(f.cx, w0.w, bb.w)))));
-                            m[4 * cq + 0] += softplus2(a0);
-                            m[4 * cq + 1] += softplus2(a1);
-                            m[4 * cq + 2] += softplus2(a2);
-                            m[4 * cq + 3] += softplus2(a3);
+                            kahan_add(m[4 * cq + 0], mc[4 * cq + 0], softplus2(a0));
+                            kahan_add(m[4 * cq + 1], mc[4 * cq + 1], softplus2(a1));
+                            kahan_add(m[4 * cq + 2], mc[4 * cq + 2], softplus2(a2));
+                            kahan_add(m[4 * cq + 3], mc[4 * cq + 3], softplus2(a3));
                         }
                     }
                 }
+                const double invnd = 1.0 / (double)n;
 #pragma unroll
-                for (int f = 0; f < 5; ++f) m0[f] = quad_sum(m0[f]) * invn;
+                for (int f = 0; f < 5; ++f) m0d[f] = quad_sum_f64((double)m0[f] - (double)m0c[f]) * invnd;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) m[c] = quad_sum(m[c]) * (kLn2 * invn);
+                for (int c = 0; c < 16; ++c)
+                    md[c] = quad_sum_f64((double)m[c] - (double)mc[c]) * (0.693147180559945309417 * invnd);
             }
 
-            // ---------------- single-particle stream (flow.py:45,51-55) and per-row contractions ------
+            // ---------------- single-particle stream (flow.py:45,51-55): forward values in float64 ------
             float Q[2][5];       // d z_i / d m0_i
             float s0own[4];      // sigma0_i for channels 4q..4q+3
             {
-                float pre[4], h4[4];
+                const double* __restrict__ P = p.params;        // flat float64 parameters (include/cgb200.h)
+                constexpr int S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
+                double h4[4];
                 {
-                    const float4 bb = b04[q];
-                    pre[0] = bb.x; pre[1] = bb.y; pre[2] = bb.z; pre[3] = bb.w;
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) {
-                        const float4 w = w0c4[f * 4 + q];
-                        pre[0] = fmaf(m0[f], w.x, pre[0]); pre[1] = fmaf(m0[f], w.y, pre[1]);
-                        pre[2] = fmaf(m0[f], w.z, pre[2]); pre[3] = fmaf(m0[f], w.w, pre[3]);
+                    double pre[4];
+                    {
+                        const double2 b01 = ldg2(P + S_B0 + 4 * q), b23 = ldg2(P + S_B0 + 4 * q + 2);
+                        pre[0] = b01.x; pre[1] = b01.y; pre[2] = b23.x; pre[3] = b23.y;
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) softplus_sigmoid(pre[k], h4[k], s0own[k]);
+                    for (int f = 0; f < 5; ++f) {
+                        const double2 w01 = ldg2(P + S_W0 + (4 + f) * 16 + 4 * q), w23 = ldg2(P + S_W0 + (4 + f) * 16 + 4 * q + 2);
+                        pre[0] = fma(m0d[f], w01.x, pre[0]); pre[1] = fma(m0d[f], w01.y, pre[1]);
+                        pre[2] = fma(m0d[f], w23.x, pre[2]); pre[3] = fma(m0d[f], w23.y, pre[3]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) softplus_sigmoid_f64(pre[k], h4[k], s0own[k]);
                 }
                 if (rv) {
                     *reinterpret_cast<float4*>(s.sig0 + row * 16 + 4 * q) = make_float4(s0own[0], s0own[1], s0own[2], s0own[3]);
-                    *reinterpret_cast<float4*>(s.hbuf + row * 20 + 4 * q) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                    double2* hd = reinterpret_cast<double2*>(s.hbuf + row * 18 + 4 * q);
+                    hd[0] = make_double2(h4[0], h4[1]);
+                    hd[1] = make_double2(h4[2], h4[3]);
                 }
                 __syncthreads();
                 if (tid < 16) {
-                    float acc = 0.f;
-                    for (int r = 0; r < n; ++r) acc += s.hbuf[r * 20 + tid];
-                    s.hbar[tid] = acc * invn;
+                    double acc = 0.0;
+#pragma unroll 4
+                    for (int r = 0; r < n; ++r) acc += s.hbuf[r * 18 + tid];
+                    s.hbar[tid] = acc / (double)n;
                 }
                 __syncthreads();
-                float g[4];
+                double g[4];
                 {
-                    const float4 bb = b14[q];
-                    g[0] = bb.x; g[1] = bb.y; g[2] = bb.z; g[3] = bb.w;
+                    const double2 b01 = ldg2(P + S_B1 + 4 * q), b23 = ldg2(P + S_B1 + 4 * q + 2);
+                    g[0] = b01.x; g[1] = b01.y; g[2] = b23.x; g[3] = b23.y;
                 }
 #pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                    const float4 hv = *reinterpret_cast<const float4*>(s.hbuf + i * 20 + 4 * e4);
-                    const float4 hb = *reinterpret_cast<const float4*>(s.hbar + 4 * e4);
-                    const float he[4] = {hv.x, hv.y, hv.z, hv.w}, hbe[4] = {hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int e = 4 * e4 + k;
-                        const float4 wa = w1a4[e * 4 + q], wb = w1b4[e * 4 + q], wc = w1c4[e * 4 + q];
-                        g[0] = fmaf(he[k], wa.x, fmaf(hbe[k], wb.x, fmaf(m[e], wc.x, g[0])));
-                        g[1] = fmaf(he[k], wa.y, fmaf(hbe[k], wb.y, fmaf(m[e], wc.y, g[1])));
-                        g[2] = fmaf(he[k], wa.z, fmaf(hbe[k], wb.z, fmaf(m[e], wc.z, g[2])));
-                        g[3] = fmaf(he[k], wa.w, fmaf(hbe[k], wb.w, fmaf(m[e], wc.w, g[3])));
-                    }
+                for (int e = 0; e < 16; ++e) {
+                    const double he = s.hbuf[i * 18 + e], hb = s.hbar[e];
+                    const double* wa = P + S_W1 + e * 16 + 4 * q;
+                    const double2 a01 = ldg2(wa), a23 = ldg2(wa + 2);
+                    const double2 b01 = ldg2(wa + 256), b23 = ldg2(wa + 258);
+                    const double2 c01 = ldg2(wa + 512), c23 = ldg2(wa + 514);
+                    g[0] = fma(he, a01.x, fma(hb, b01.x, fma(md[e], c01.x, g[0])));
+                    g[1] = fma(he, a01.y, fma(hb, b01.y, fma(md[e], c01.y, g[1])));
+                    g[2] = fma(he, a23.x, fma(hb, b23.x, fma(md[e], c23.x, g[2])));
+                    g[3] = fma(he, a23.y, fma(hb, b23.y, fma(md[e], c23.y, g[3])));
                 }
-                float s1own[4], dzx = 0.f, dzy = 0.f;
+                float s1own[4];
+                double dzx = 0.0, dzy = 0.0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float sp;
-                    softplus_sigmoid(g[k], sp, s1own[k]);
-                    const float sv = h4[k] + sp;                  // s_i (flow.py:52)
-                    dzx = fmaf(sv, wf[(4 * q + k) * 2 + 0], dzx);
-                    dzy = fmaf(sv, wf[(4 * q + k) * 2 + 1], dzy);
+                    double sp;
+                    softplus_sigmoid_f64(g[k], sp, s1own[k]);
+                    const double sv = h4[k] + sp;                 // s_i (flow.py:52)
+                    const double2 wfv = ldg2(P + S_WF + (4 * q + k) * 2);
+                    dzx = fma(sv, wfv.x, dzx);
+                    dzy = fma(sv, wfv.y, dzy);
                 }
-                dzx = quad_sum(dzx);
-                dzy = quad_sum(dzy);
-                if (rv && q == 0) s.dz[row] = make_float2(dzx, dzy);
-                // WfS[e][a] = Wf[e][a] * sigma1_i[e]
+                dzx = quad_sum_f64(dzx);
+                dzy = quad_sum_f64(dzy);
+                if (rv && q == 0) s.dz[row] = make_double2(dzx, dzy);
+                // ---- Jacobian-side contractions, FP32:  WfS[e][a] = Wf[e][a] * sigma1_i[e]
                 float wfs[16][2];
                 {
                     const int gbase = lane & ~3;
@@ -406,7 +438,8 @@ sweep_kernel(const SweepParams p) {
                         }
                         if (rv) {
                             float* jp = s.J + (2 * row) * pJ + 2 * k;
-                            jp[0] = j00; jp[1] = j01; jp[pJ] = j10; jp[pJ + 1] = j11;
+                            *reinterpret_cast<float2*>(jp) = make_float2(j00, j01);
+                            *reinterpret_cast<float2*>(jp + pJ) = make_float2(j10, j11);
                         }
                         rs[0] += j00; rs[1] += j01; rs[2] += j10; rs[3] += j11;
                     }
@@ -493,8 +526,11 @@ sweep_kernel(const SweepParams p) {
                             t11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, t11));
                         }
                         if (rv) {
-                            float* jp = s.J + (2 * row) * pJ + 2 * k;
-                            jp[0] += t00; jp[1] += t01; jp[pJ] += t10; jp[pJ + 1] += t11;
+                            float2* j0 = reinterpret_cast<float2*>(s.J + (2 * row) * pJ + 2 * k);
+                            float2* j1 = reinterpret_cast<float2*>(s.J + (2 * row + 1) * pJ + 2 * k);
+                            float2 v0 = *j0, v1 = *j1;
+                            v0.x += t00; v0.y += t01; v1.x += t10; v1.y += t11;
+                            *j0 = v0; *j1 = v1;
                         }
                         rs[0] += t00; rs[1] += t01; rs[2] += t10; rs[3] += t11;
                     }
@@ -513,21 +549,26 @@ sweep_kernel(const SweepParams p) {
                 __syncthreads();
             }
 
-            // ---------------- LU phase: real 2n x 2n (warps [0,nJw)) || complex n x n (next nDw warps) --
+            // ---------------- LU phase: real 2n x 2n FP32 (warps [0,nJw)) || complex n x n FP64 (warps >= nJw) --
             if (warp < nJw) {
                 const int r = tid;
                 const bool active = r < N2;
                 float* base = s.J + (active ? r : 0) * pJ;
+                const int nq4 = pJ >> 2;
                 bool done = !active;
                 float mylog = 0.f;
                 float cur = active ? base[0] : 0.f;          // a[r][k] for the current k
                 for (int k = 0; k < N2; ++k) {
                     const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
                     const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                    if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
-                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
-                    unsigned gmax = s.redJ[(k & 1) * 8];
-                    for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
+                    unsigned gmax = wmax;
+                    if (nJw > 1) {
+                        if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
+                        named_bar_sync(1, nJw * 32);
+                        for (int w = 0; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
+                    } else {
+                        __syncwarp();
+                    }
                     const int pr = (int)(gmax & 0x7Fu);
                     const float* prow = s.J + pr * pJ;
                     const float piv = prow[k];
@@ -535,80 +576,98 @@ sweep_kernel(const SweepParams p) {
                         done = true;
                         mylog = lg2_approx(fabsf(piv));
                     } else if (!done) {
+                        // any multiplier leaves the determinant unchanged; the approximate reciprocal only
+                        // perturbs the eliminated (never re-read) entry at the 1e-7 level
                         const float l = -cur * rcp_approx(piv);
-                        // 1 Newton step on the reciprocal is not needed: any l gives the same determinant
-                        // up to the rounding of this row operation; keep the approx reciprocal.
-                        for (int j = k + 1; j < N2; ++j) base[j] = fmaf(l, prow[j], base[j]);
+                        const float4* p4 = reinterpret_cast<const float4*>(prow);
+                        float4* b4 = reinterpret_cast<float4*>(base);
+#pragma unroll 2
+                        for (int j4 = (k + 1) >> 2; j4 < nq4; ++j4) {
+                            const float4 pv = p4[j4];
+                            float4 v = b4[j4];
+                            v.x = fmaf(l, pv.x, v.x); v.y = fmaf(l, pv.y, v.y);
+                            v.z = fmaf(l, pv.z, v.z); v.w = fmaf(l, pv.w, v.w);
+                            b4[j4] = v;
+                        }
                         if (k + 1 < N2) cur = base[k + 1];
                     }
+                    if (nJw == 1) __syncwarp();
                 }
                 // sum log2|pivot| over rows (one pivot per row)
                 double acc = (double)mylog;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) s.lsum[warp] = acc;
-            } else if (warp < nJw + nDw) {
-                const int dw = warp - nJw;
-                const int r = tid - nJw * 32;
-                const bool active = r < n;
-                float2* base = s.D + (active ? r : 0) * pD;
-                // build row r of D_rj = exp(2 pi i m_j . w_r)  (src/slater.py:14-17; twist and the common
-                // displacement are pure row/column phases and drop out of |det|)
-                if (active) {
-                    float mx = 0.f, my = 0.f;
-                    for (int t = 0; t < n; ++t) { const float2 v = s.dz[t]; mx += v.x; my += v.y; }
-                    const float2 dzi = s.dz[r];
-                    const float4 wp = s.wpar[r];
-                    const float whx = wp.x, wlx = fmaf(dzi.x - mx * invn, invLf, wp.y);
-                    const float why = wp.z, wly = fmaf(dzi.y - my * invn, invLf, wp.w);
-                    for (int j = 0; j < n; ++j) {
+                if (lane == 0) s.lsum[warp] = acc * 0.693147180559945309417;
+            } else {
+                // ---- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + (dz - mean dz)/L
+                // (src/slater.py:14-17; the twist and the common displacement are pure row/column phases
+                // and drop out of |det|).  All warps >= nJw build entries; the first nDw of them factorise.
+                const int t2 = tid - nJw * 32, nb = (NW - nJw) * 32;
+                {
+                    double mx = 0.0, my = 0.0;
+                    for (int t = 0; t < n; ++t) { const double2 v = s.dz[t]; mx += v.x; my += v.y; }
+                    mx /= (double)n; my /= (double)n;
+                    for (int idx = t2; idx < n * n; idx += nb) {
+                        const int rr = idx / n, j = idx - rr * n;
+                        const double2 uu = s.us[rr], dd = s.dz[rr];
+                        const double wx = fma(dd.x - mx, invL, uu.x), wy = fma(dd.y - my, invL, uu.y);
                         const float2 mk = s.kint[j];
-                        float phx = mk.x * whx, ehx = fmaf(mk.x, whx, -phx);
-                        float phy = mk.y * why, ehy = fmaf(mk.y, why, -phy);
-                        phx -= rintf(phx);
-                        phy -= rintf(phy);
-                        const float lo = fmaf(mk.x, wlx, fmaf(mk.y, wly, ehx + ehy));
-                        float sn, cs;
-                        sincospif(2.f * ((phx + phy) + lo), &sn, &cs);
-                        base[j] = make_float2(cs, sn);
+                        double ph = fma((double)mk.x, wx, (double)mk.y * wy);
+                        ph -= rint(ph);
+                        double sn, cs;
+                        sincospi(2.0 * ph, &sn, &cs);
+                        s.D[rr * pD + j] = make_double2(cs, sn);
                     }
                 }
-                bool done = !active;
-                float mylog = 0.f;
-                float2 cur = active ? base[0] : make_float2(0.f, 0.f);
-                for (int k = 0; k < n; ++k) {
-                    const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur.x) + fabsf(cur.y)) & ~0x7Fu) | (unsigned)r);
-                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                    if (lane == 0) s.redD[(k & 1) * 8 + dw] = wmax;
-                    if (nDw > 1) named_bar_sync(2, nDw * 32); else __syncwarp();
-                    unsigned gmax = s.redD[(k & 1) * 8];
-                    for (int w = 1; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
-                    const int pr = (int)(gmax & 0x7Fu);
-                    const float2* prow = s.D + pr * pD;
-                    const float2 piv = prow[k];
-                    const float pn = fmaf(piv.x, piv.x, piv.y * piv.y);
-                    if (r == pr) {
-                        done = true;
-                        mylog = 0.5f * lg2_approx(pn);
-                    } else if (!done) {
-                        // l = -cur / piv
-                        const float ip = rcp_approx(pn);
-                        const float lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
-                        const float ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
-                        for (int j = k + 1; j < n; ++j) {
-                            const float2 pv = prow[j];
-                            float2 v = base[j];
-                            v.x = fmaf(lx, pv.x, fmaf(-ly, pv.y, v.x));
-                            v.y = fmaf(lx, pv.y, fmaf(ly, pv.x, v.y));
-                            base[j] = v;
+                if (NW - nJw > 1) named_bar_sync(3, nb); else __syncwarp();
+                if (warp < nJw + nDw) {
+                    const int dw = warp - nJw;
+                    const int r = t2;
+                    const bool active = r < n;
+                    double2* base = s.D + (active ? r : 0) * pD;
+                    bool done = !active;
+                    double mylog = 0.0;
+                    double2 cur = active ? base[0] : make_double2(0.0, 0.0);
+                    for (int k = 0; k < n; ++k) {
+                        const float mag = (float)(fabs(cur.x) + fabs(cur.y));
+                        const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
+                        const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                        unsigned gmax = wmax;
+                        if (nDw > 1) {
+                            if (lane == 0) s.redD[(k & 1) * 8 + dw] = wmax;
+                            named_bar_sync(2, nDw * 32);
+                            for (int w = 0; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                        } else {
+                            __syncwarp();
                         }
-                        if (k + 1 < n) cur = base[k + 1];
+                        const int pr = (int)(gmax & 0x7Fu);
+                        const double2* prow = s.D + pr * pD;
+                        const double2 piv = prow[k];
+                        const double pn = fma(piv.x, piv.x, piv.y * piv.y);
+                        if (r == pr) {
+                            done = true;
+                            mylog = 0.5 * log(pn);
+                        } else if (!done) {
+                            const double ip = 1.0 / pn;            // l = -cur / piv
+                            const double lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
+                            const double ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
+#pragma unroll 2
+                            for (int j = k + 1; j < n; ++j) {
+                                const double2 pv = prow[j];
+                                double2 v = base[j];
+                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                base[j] = v;
+                            }
+                            if (k + 1 < n) cur = base[k + 1];
+                        }
+                        if (nDw == 1) __syncwarp();
                     }
-                }
-                double acc = (double)mylog;
+                    double acc = mylog;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) s.lsum[warp] = acc;
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) s.lsum[warp] = acc;
+                }
             }
             __syncthreads();
 
@@ -617,9 +676,7 @@ sweep_kernel(const SweepParams p) {
                 double ldJ = 0.0, ldD = 0.0;
                 for (int w = 0; w < nJw; ++w) ldJ += s.lsum[w];
                 for (int w = nJw; w < nJw + nDw; ++w) ldD += s.lsum[w];
-                const double ln2 = 0.693147180559945309417;
-                ldJ *= ln2;
-                ldD = ldD * ln2 - (double)n * log(p.L);          // D carries L^{-dim/2} per entry (slater.py:17)
+                ldD -= (double)n * log(p.L);                     // D carries L^{-dim/2} per entry (slater.py:17)
                 const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179
                 int acc = 1;
                 if (step == 0) {
