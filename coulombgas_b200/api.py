@@ -118,8 +118,16 @@ class Logp:
         if d not in self._ws:
             nbytes = ctypes.c_size_t()
             check(lib.cgb_logp_workspace_bytes(B, n, ctypes.byref(nbytes)), "cgb_logp_workspace_bytes")
-            self._ws[d] = torch.empty(nbytes.value, dtype=torch.uint8, device=_dev())
+            self._ws[d] = torch.zeros(nbytes.value, dtype=torch.uint8, device=_dev())
         return self._ws[d]
+
+    def fallback_count(self):
+        """Cumulative number of log p evaluations (this device/stream workspace) whose Jacobian left the safe range
+        of the unpivoted 2x2-block LU and were redone with the partially pivoted LU."""
+        d = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        if d not in self._ws:
+            return 0
+        return int(self._ws[d][4096:4104].view(torch.int64).item())
 
     def __call__(self, x, params, state_idx, return_parts=False, return_jac=False):
         xd, was_np = _to_dev(x, torch.float64)

@@ -1,5 +1,6 @@
 // C ABI of libcgb200.so (include/cgb200.h): argument checking, host-side table preparation, launches.
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 #include <utility>
 #include "cgb_internal.h"
@@ -64,11 +65,12 @@ int cgb_ewald_prepare_host(const int64_t* G, int nG, double kappa, float* items_
 }
 
 static size_t wpack_bytes() { return ((sizeof(float) * W_TOTAL) + 255) & ~size_t(255); }
+static size_t workspace_total() { return wpack_bytes() + 256; }   // + cumulative pivot-fallback counter (uint64)
 
 int cgb_logp_workspace_bytes(int B, int n, size_t* bytes) {
     if (!bytes || B < 0) return CGB_E_BADARG;
     if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
-    *bytes = wpack_bytes();
+    *bytes = workspace_total();
     return CGB_OK;
 }
 int cgb_mcmc_workspace_bytes(int B, int n, size_t* bytes) { return cgb_logp_workspace_bytes(B, n, bytes); }
@@ -83,7 +85,7 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
         return CGB_E_BADARG;
     if ((noise == nullptr) != (uniforms == nullptr)) return CGB_E_BADARG;
     if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
-    if (!workspace || workspace_bytes < wpack_bytes() || ((uintptr_t)workspace & 15)) return CGB_E_WORKSPACE;
+    if (!workspace || workspace_bytes < workspace_total() || ((uintptr_t)workspace & 15)) return CGB_E_WORKSPACE;
     if ((uintptr_t)params & 15) return CGB_E_BADARG;            // float64 parameters are read as 16-byte pairs
     if (B == 0) return CGB_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -95,6 +97,9 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     p.noise = noise; p.uniforms = uniforms; p.seed = seed; p.mc_steps = mc_steps; p.sigma = sigma; p.L = L;
     p.B = B; p.n = n; p.wrap = wrap; p.out_logp = out_logp; p.out_naccept = out_naccept;
     p.out_acc_trace = acc_trace; p.out_logp_trace = logp_trace; p.out_parts = out_parts; p.out_jac = out_jac;
+    const char* fp = getenv("CGB_FORCE_PIVOT");                    // debug knob: exercise the pivoted fallback LU
+    p.force_pivot = (fp && fp[0] == '1') ? 1 : 0;
+    p.fallback_counter = (unsigned long long*)((char*)workspace + wpack_bytes());
     return launch_sweep(p, st);
 }
 

@@ -43,6 +43,8 @@ struct SweepParams {
     double* out_logp_trace;   // (S+1,B) or null
     double* out_parts;        // (B,2) or null
     float* out_jac;           // (B,2n,2n) or null
+    int force_pivot;          // debug: always use the pivoted scalar LU for the Jacobian
+    unsigned long long* fallback_counter;   // evaluations redone with the pivoted LU (in the workspace)
 };
 
 inline int sweep_num_warps(int n) { int w = (n + 7) / 8; return w < 2 ? 2 : w; }

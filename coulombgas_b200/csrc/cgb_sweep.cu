@@ -38,60 +38,43 @@ __global__ void prep_params_kernel(const double* __restrict__ p, float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct Smem {
-    float* wts;      // W_TOTAL
-    double* xs;      // 2n   current walker
-    double* xp;      // 2n   proposal
-    float4* pos;     // n8   (cos, sin) of half angles pi*u for x and y
-    double2* us;     // n8   reduced coordinates u = frac(x/L), float64
-    float2* kint;    // n8   integer part of the occupied k rows
-    double2* dz;     // n8   backflow displacement (s_i Wf) in float64, common mode still included
-    float* sig0;     // n8*16
-    double* hbuf;    // n8*18  h_i in float64
-    double* hbar;    // 16
-    float* Rbuf;     // n8*36  (aliases D)
-    float* Tbuf;     // n8*36
-    float* Hbuf;     // n8*36
-    float* J;        // 2n * pitchJ   (pitchJ = 4*odd: conflict-free LDS.128 by row)
-    double2* D;      // n * pitchD complex float64 (aliases Rbuf/Tbuf)
-    unsigned* redJ;  // 2*8
-    unsigned* redD;  // 2*8
-    double* lsum;    // 16
-    int* flag;       // 4
-    int pitchJ, pitchD;
+// Shared-memory layout.  Everything whose size depends only on the row-slot count N8 = 8*NW sits at
+// compile-time offsets; the two matrices (sizes depend on the run-time n) come last.
+template <int N8>
+struct Lay {
+    static constexpr int o_xs = 0;                    // double[2*N8]   current walker
+    static constexpr int o_xp = o_xs + 16 * N8;       // double[2*N8]   proposal
+    static constexpr int o_ls = o_xp + 16 * N8;       // double[16]     log-det partial sums
+    static constexpr int o_hb = o_ls + 128;           // double[16]     mean_k h_k
+    static constexpr int o_us = o_hb + 128;           // double2[N8]    reduced coordinates u = frac(x/L)
+    static constexpr int o_dz = o_us + 16 * N8;       // double2[N8]    backflow displacement s_i Wf (float64)
+    static constexpr int o_w = o_dz + 16 * N8;        // float[W_TOTAL] FP32 weight pack
+    static constexpr int o_k = o_w + 4 * W_TOTAL;     // int2[N8]       integer part of the occupied k rows
+    static constexpr int o_pos = o_k + 8 * N8;        // float4[N8]     (cos,sin) of the half angles pi*u
+    static constexpr int o_s0 = o_pos + 16 * N8;      // float[N8*16]   sigma0
+    // [o_pos, o_red) = pos | sigma0 | H is dead once pass 3 is done: the Slater power tables alias it
+    static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 144 * N8;
+    static constexpr int o_H = o_s0 + 64 * N8;        // float[N8*36] H_k   (aliases double[N8*18] h_i: dead before H is written)
+    static constexpr int o_red = o_H + 144 * N8;      // unsigned[2*8] J pivots, unsigned[2*8] D pivots, int[4] flags
+    static constexpr int o_J = o_red + 160;           // float4[n*pitchB] Jacobian as 2x2 blocks; then max(R|T float[2*N8*36], D double2[n*pitchD])
+    static_assert(o_J % 16 == 0, "alignment");
 };
+__host__ __device__ inline int pitch_B(int n) { return n | 1; }   // float4 blocks per block-row, odd: conflict-free LDS.128
+__host__ __device__ inline int pitch_D(int n) { return n | 1; }                          // odd: conflict-free 16-byte rows
 
-__host__ __device__ inline size_t smem_carve(int n, int n8, Smem* s, unsigned char* base) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-    const int pitchJ = 4 * (((2 * n + 3) / 4) | 1), pitchD = n | 1;
-    const size_t o_xs = take(sizeof(double) * 2 * n), o_xp = take(sizeof(double) * 2 * n);
-    const size_t o_ls = take(sizeof(double) * 16);
-    const size_t o_w = take(sizeof(float) * W_TOTAL);
-    const size_t o_pos = take(sizeof(float4) * n8), o_us = take(sizeof(double2) * n8);
-    const size_t o_k = take(sizeof(float2) * n8), o_dz = take(sizeof(double2) * n8);
-    const size_t o_s0 = take(sizeof(float) * n8 * 16), o_h = take(sizeof(double) * n8 * 18);
-    const size_t o_hb = take(sizeof(double) * 16);
-    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(double2) * n * pitchD;
-    const size_t o_rt = take(rt > dd ? rt : dd);
-    const size_t o_H = take(sizeof(float) * n8 * 36);
-    const size_t o_J = take(sizeof(float) * 2 * n * pitchJ);
-    const size_t o_rj = take(sizeof(unsigned) * 16), o_rd = take(sizeof(unsigned) * 16);
-    const size_t o_f = take(sizeof(int) * 4);
-    if (s) {
-        s->xs = (double*)(base + o_xs); s->xp = (double*)(base + o_xp); s->lsum = (double*)(base + o_ls);
-        s->wts = (float*)(base + o_w); s->pos = (float4*)(base + o_pos); s->us = (double2*)(base + o_us);
-        s->kint = (float2*)(base + o_k); s->dz = (double2*)(base + o_dz);
-        s->sig0 = (float*)(base + o_s0); s->hbuf = (double*)(base + o_h); s->hbar = (double*)(base + o_hb);
-        s->Rbuf = (float*)(base + o_rt); s->Tbuf = s->Rbuf + n8 * 36; s->D = (double2*)(base + o_rt);
-        s->Hbuf = (float*)(base + o_H); s->J = (float*)(base + o_J);
-        s->redJ = (unsigned*)(base + o_rj); s->redD = (unsigned*)(base + o_rd); s->flag = (int*)(base + o_f);
-        s->pitchJ = pitchJ; s->pitchD = pitchD;
-    }
-    return off;
+size_t sweep_smem_bytes(int n) {
+    const int n8 = 8 * sweep_num_warps(n);
+    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160);
+    const size_t jb = sizeof(float4) * n * pitch_B(n);
+    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(double2) * n * pitch_D(n);
+    return fixed + jb + (rt > dd ? rt : dd);
 }
 
-size_t sweep_smem_bytes(int n) { return smem_carve(n, 8 * sweep_num_warps(n), nullptr, nullptr); }
+struct Smem {
+    float* wts; double* xs; double* xp; float4* pos; double2* us; int2* kint; double2* ptab; double2* dz; float* sig0;
+    double* hbuf; double* hbar; float* Rbuf; float* Tbuf; float* Hbuf; float4* J; double2* D;
+    unsigned* redJ; unsigned* redD; double* lsum; int* flag;
+};
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -157,10 +140,22 @@ sweep_kernel(const SweepParams p) {
     const bool rv = row < n;
     const int i = rv ? row : n - 1;
     constexpr int n8 = 8 * NW;
+    using L_ = Lay<n8>;
+    static_assert(L_::o_J == 16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160, "host size formula");
+    const int N2 = 2 * n, pB = pitch_B(n), pD = pitch_D(n);
     Smem s;
-    smem_carve(n, n8, &s, smem_raw);
-    const int N2 = 2 * n, pJ = s.pitchJ, pD = s.pitchD;
-    const int nJw = (N2 + 31) >> 5, nDw = (n + 31) >> 5;     // LU warps: J on [0,nJw), D on [nJw, nJw+nDw)
+    s.xs = (double*)(smem_raw + L_::o_xs); s.xp = (double*)(smem_raw + L_::o_xp); s.lsum = (double*)(smem_raw + L_::o_ls);
+    s.hbar = (double*)(smem_raw + L_::o_hb); s.us = (double2*)(smem_raw + L_::o_us); s.dz = (double2*)(smem_raw + L_::o_dz);
+    s.wts = (float*)(smem_raw + L_::o_w); s.pos = (float4*)(smem_raw + L_::o_pos); s.kint = (int2*)(smem_raw + L_::o_k); s.ptab = (double2*)(smem_raw + L_::o_pos);
+    s.sig0 = (float*)(smem_raw + L_::o_s0); s.Hbuf = (float*)(smem_raw + L_::o_H); s.hbuf = (double*)(smem_raw + L_::o_H);
+    s.redJ = (unsigned*)(smem_raw + L_::o_red); s.redD = s.redJ + 16; s.flag = (int*)(s.redJ + 32);
+    s.J = (float4*)(smem_raw + L_::o_J);     // block (i,k) = (J[2i][2k], J[2i][2k+1], J[2i+1][2k], J[2i+1][2k+1])
+    s.Rbuf = (float*)(s.J + n * pB); s.Tbuf = s.Rbuf + n8 * 36; s.D = (double2*)s.Rbuf;
+    // LU warps: Jacobian on [0,nJw), Slater on [nJw, nJw+nDw); both counts follow from NW = ceil(n/8)
+    constexpr int nJw = (NW + 1) / 2, nDw = NW >= 5 ? 2 : 1;
+    constexpr int nBw = nDw;          // warps of the block-LU fast path (one thread per 2x2 block-row)
+    constexpr int nSw = NW - nJw;     // warps that build the Slater matrix; the first nDw of them factorise it
+    static_assert(nJw + nDw <= NW, "warp roles");
     const float invn = 1.f / (float)n;
     const double invL = 1.0 / p.L;
     const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
@@ -179,17 +174,24 @@ sweep_kernel(const SweepParams p) {
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
+        if (tid == 0) s.flag[1] = 0;
         if (tid < N2) s.xs[tid] = p.x[(size_t)b * N2 + tid];
+        __syncthreads();
         if (tid < n) {
             int si = p.state_idx[(size_t)b * n + tid];
             si = min(max(si, 0), p.M - 1);
-            s.kint[tid] = make_float2((float)rint(p.ktable[2 * si] - p.tw0), (float)rint(p.ktable[2 * si + 1] - p.tw1));
+            const int mx = (int)rint(p.ktable[2 * si] - p.tw0), my = (int)rint(p.ktable[2 * si + 1] - p.tw1);
+            s.kint[tid] = make_int2(mx, my);
+            atomicMax(&s.flag[1], max(abs(mx), abs(my)));
         }
         double logp_cur = 0.0;   // thread 0 only
         int nacc = 0;            // thread 0 only
 
         for (int step = 0; step <= p.mc_steps; ++step) {
+          bool use_pivot = p.force_pivot != 0;
+          for (;;) {           // at most two passes: unpivoted block LU, then (rarely) the pivoted fallback
             __syncthreads();
+            if (tid == 0) s.flag[2] = 0;
             // ---------------- stage 0: proposal (MCMC.py:26) and reduced coordinates ----------------
             if (tid < N2) {
                 double xv = s.xs[tid];
@@ -390,8 +392,8 @@ sweep_kernel(const SweepParams p) {
                     *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 4 * q) = make_float4(Tq[0][0], Tq[0][1], Tq[0][2], Tq[0][3]);
                     *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 16 + 4 * q) = make_float4(Tq[1][0], Tq[1][1], Tq[1][2], Tq[1][3]);
                 }
-                __syncwarp();
             }
+            __syncthreads();     // h_i (aliased by H) and the R/T rows are complete before the pair passes touch them
 
             // ---------------- pass 2: local Jacobian blocks and the mean-field accumulators ----------
             float rs[4] = {0.f, 0.f, 0.f, 0.f};      // partial row sum of the off-diagonal blocks
@@ -436,11 +438,7 @@ sweep_kernel(const SweepParams p) {
                                 j10 = fmaf(R[1][c], fx, j10); j11 = fmaf(R[1][c], fy, j11);
                             }
                         }
-                        if (rv) {
-                            float* jp = s.J + (2 * row) * pJ + 2 * k;
-                            *reinterpret_cast<float2*>(jp) = make_float2(j00, j01);
-                            *reinterpret_cast<float2*>(jp + pJ) = make_float2(j10, j11);
-                        }
+                        if (rv) s.J[row * pB + k] = make_float4(j00, j01, j10, j11);
                         rs[0] += j00; rs[1] += j01; rs[2] += j10; rs[3] += j11;
                     }
                 }
@@ -526,11 +524,9 @@ sweep_kernel(const SweepParams p) {
                             t11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, t11));
                         }
                         if (rv) {
-                            float2* j0 = reinterpret_cast<float2*>(s.J + (2 * row) * pJ + 2 * k);
-                            float2* j1 = reinterpret_cast<float2*>(s.J + (2 * row + 1) * pJ + 2 * k);
-                            float2 v0 = *j0, v1 = *j1;
-                            v0.x += t00; v0.y += t01; v1.x += t10; v1.y += t11;
-                            *j0 = v0; *j1 = v1;
+                            float4 v = s.J[row * pB + k];
+                            v.x += t00; v.y += t01; v.z += t10; v.w += t11;
+                            s.J[row * pB + k] = v;
                         }
                         rs[0] += t00; rs[1] += t01; rs[2] += t10; rs[3] += t11;
                     }
@@ -538,72 +534,136 @@ sweep_kernel(const SweepParams p) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) rs[t] = quad_sum(rs[t]);
                 if (rv && q == 0) {          // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
-                    float* jp = s.J + (2 * row) * pJ + 2 * row;
-                    jp[0] = 1.f - rs[0]; jp[1] = -rs[1]; jp[pJ] = -rs[2]; jp[pJ + 1] = 1.f - rs[3];
+                    s.J[row * pB + row] = make_float4(1.f - rs[0], -rs[1], -rs[2], 1.f - rs[3]);
                 }
             }
             __syncthreads();
             if (p.out_jac && step == 0) {
                 float* oj = p.out_jac + (size_t)b * N2 * N2;
-                for (int t = tid; t < N2 * N2; t += NW * 32) oj[t] = s.J[(t / N2) * pJ + (t % N2)];
+                for (int t = tid; t < N2 * N2; t += NW * 32) {
+                    const int rr = t / N2, cc = t - rr * N2;
+                    oj[t] = reinterpret_cast<const float*>(s.J)[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)];
+                }
                 __syncthreads();
             }
 
-            // ---------------- LU phase: real 2n x 2n FP32 (warps [0,nJw)) || complex n x n FP64 (warps >= nJw) --
-            if (warp < nJw) {
+            // ---------------- LU phase: real 2n x 2n FP32 Jacobian || complex n x n FP64 Slater matrix ---------
+            // Jacobian: J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU, one
+            // thread per block-row (2 rows), blocks in shared memory: log|det J| = sum_k log|det P_kk|.  Half the
+            // sequential depth of a scalar LU, no pivot search, no cross-warp exchange.  Multipliers and pivot
+            // determinants are monitored; if they leave the safe range the whole evaluation is redone with the
+            // partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
+            if (!use_pivot && warp < nBw) {
+                const int bi = tid;
+                const bool act = bi < n;
+                float4* brow = s.J + (act ? bi : 0) * pB;
+                float lacc = 0.f;
+                bool bad = false;
+                for (int k = 0; k < n; ++k) {
+                    if (nBw > 1) named_bar_sync(1, nBw * 32); else __syncwarp();
+                    const float4* prow = s.J + k * pB;
+                    const float4 pk = prow[k];                              // pivot block (broadcast)
+                    const float det = pk.x * pk.w - pk.y * pk.z;
+                    const float idet = rcp_approx(det);
+                    lacc += lg2_approx(fabsf(det));                          // identical in every lane
+                    bad |= !(fabsf(det) > 0.05f);                            // also catches NaN
+                    if (act && bi > k) {
+                        const float4 a = brow[k];
+                        // -L = -A_ik P_kk^{-1},  P^{-1} = [[w,-y],[-z,x]] / det
+                        const float l00 = (a.y * pk.z - a.x * pk.w) * idet, l01 = (a.x * pk.y - a.y * pk.x) * idet;
+                        const float l10 = (a.w * pk.z - a.z * pk.w) * idet, l11 = (a.z * pk.y - a.w * pk.x) * idet;
+                        bad |= (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
+#pragma unroll 4
+                        for (int j = k + 1; j < n; ++j) {
+                            const float4 qv = prow[j];
+                            float4 v = brow[j];
+                            v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
+                            v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
+                            v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
+                            v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
+                            brow[j] = v;
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, bad) && lane == 0) s.flag[2] = 1;
+                if (tid == 0) s.lsum[0] = (double)lacc * 0.693147180559945309417;
+            } else if (use_pivot && warp < nJw) {
+                // ---- fallback: scalar LU with partial pivoting on the blocked storage, one thread per row.
+                // |a| bits with the row id in the low 7 bits -> one REDUX per warp; per-warp maxima exchanged
+                // through a double-buffered slot, one named barrier per elimination step.
                 const int r = tid;
-                const bool active = r < N2;
-                float* base = s.J + (active ? r : 0) * pJ;
-                const int nq4 = pJ >> 2;
-                bool done = !active;
+                float* Jf = reinterpret_cast<float*>(s.J);
+                auto el = [&](int rr, int cc) -> float& { return Jf[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)]; };
+                bool done = !(r < N2);
                 float mylog = 0.f;
-                float cur = active ? base[0] : 0.f;          // a[r][k] for the current k
                 for (int k = 0; k < N2; ++k) {
+                    const float cur = done ? 0.f : el(r, k);
                     const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
                     const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                    unsigned gmax = wmax;
-                    if (nJw > 1) {
-                        if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
-                        named_bar_sync(1, nJw * 32);
-                        for (int w = 0; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
-                    } else {
-                        __syncwarp();
-                    }
+                    if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
+                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
+                    unsigned gmax = s.redJ[(k & 1) * 8];
+#pragma unroll
+                    for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
                     const int pr = (int)(gmax & 0x7Fu);
-                    const float* prow = s.J + pr * pJ;
-                    const float piv = prow[k];
+                    const float piv = el(pr, k);
                     if (r == pr) {
                         done = true;
                         mylog = lg2_approx(fabsf(piv));
                     } else if (!done) {
-                        // any multiplier leaves the determinant unchanged; the approximate reciprocal only
-                        // perturbs the eliminated (never re-read) entry at the 1e-7 level
-                        const float l = -cur * rcp_approx(piv);
-                        const float4* p4 = reinterpret_cast<const float4*>(prow);
-                        float4* b4 = reinterpret_cast<float4*>(base);
-#pragma unroll 2
-                        for (int j4 = (k + 1) >> 2; j4 < nq4; ++j4) {
-                            const float4 pv = p4[j4];
-                            float4 v = b4[j4];
-                            v.x = fmaf(l, pv.x, v.x); v.y = fmaf(l, pv.y, v.y);
-                            v.z = fmaf(l, pv.z, v.z); v.w = fmaf(l, pv.w, v.w);
-                            b4[j4] = v;
-                        }
-                        if (k + 1 < N2) cur = base[k + 1];
+                        const float l = -cur / piv;
+                        for (int j = k + 1; j < N2; ++j) el(r, j) = fmaf(l, el(pr, j), el(r, j));
                     }
-                    if (nJw == 1) __syncwarp();
+                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
                 }
-                // sum log2|pivot| over rows (one pivot per row)
                 double acc = (double)mylog;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) s.lsum[warp] = acc * 0.693147180559945309417;
-            } else {
+                if (lane == 0) s.lsum[8 + warp] = acc * 0.693147180559945309417;
+            }
+            if (warp >= NW - nSw) {
                 // ---- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + (dz - mean dz)/L
                 // (src/slater.py:14-17; the twist and the common displacement are pure row/column phases
                 // and drop out of |det|).  All warps >= nJw build entries; the first nDw of them factorise.
-                const int t2 = tid - nJw * 32, nb = (NW - nJw) * 32;
-                {
+                constexpr int nb = nSw * 32;
+                const int t2 = tid - nJw * 32;
+                const int mmax = s.flag[1];                      // max |m| over this walker's occupied orbitals
+                if (mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes) {
+                    // power tables  X_r^m = e^{2 pi i m w_rx},  Y_r^m,  m = 1..mmax  (one sincospi per coordinate)
+                    for (int c = t2; c < 2 * n; c += nb) {
+                        const int rr = c >> 1, comp = c & 1;
+                        double mean = 0.0;
+                        for (int t = 0; t < n; ++t) mean += reinterpret_cast<const double*>(s.dz)[2 * t + comp];
+                        mean /= (double)n;
+                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[c] - mean, invL,
+                                              reinterpret_cast<const double*>(s.us)[c]);
+                        double sn, cs;
+                        sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
+                        double2* tb = s.ptab + (size_t)c * mmax;   // [row][comp][m-1]
+                        double2 pw = make_double2(cs, sn);
+                        tb[0] = pw;
+                        for (int m = 1; m < mmax; ++m) {
+                            pw = make_double2(pw.x * cs - pw.y * sn, pw.x * sn + pw.y * cs);
+                            tb[m] = pw;
+                        }
+                    }
+                    if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
+                    for (int j = t2 >> 5; j < n; j += nb / 32) {
+                        const int rr = t2 & 31;
+                        const int2 mk = s.kint[j];
+#pragma unroll
+                        for (int half = 0; half < (NW > 4 ? 2 : 1); ++half) {
+                            const int r2 = rr + 32 * half;
+                            if (r2 < n) {
+                                const int ax = abs(mk.x), ay = abs(mk.y);
+                                double2 X = make_double2(1.0, 0.0), Y = make_double2(1.0, 0.0);
+                                if (ax) { X = s.ptab[(size_t)(2 * r2) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
+                                if (ay) { Y = s.ptab[(size_t)(2 * r2 + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
+                                s.D[r2 * pD + j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                            }
+                        }
+                    }
+                } else {
                     double mx = 0.0, my = 0.0;
                     for (int t = 0; t < n; ++t) { const double2 v = s.dz[t]; mx += v.x; my += v.y; }
                     mx /= (double)n; my /= (double)n;
@@ -611,7 +671,7 @@ sweep_kernel(const SweepParams p) {
                         const int rr = idx / n, j = idx - rr * n;
                         const double2 uu = s.us[rr], dd = s.dz[rr];
                         const double wx = fma(dd.x - mx, invL, uu.x), wy = fma(dd.y - my, invL, uu.y);
-                        const float2 mk = s.kint[j];
+                        const int2 mk = s.kint[j];
                         double ph = fma((double)mk.x, wx, (double)mk.y * wy);
                         ph -= rint(ph);
                         double sn, cs;
@@ -619,23 +679,26 @@ sweep_kernel(const SweepParams p) {
                         s.D[rr * pD + j] = make_double2(cs, sn);
                     }
                 }
-                if (NW - nJw > 1) named_bar_sync(3, nb); else __syncwarp();
+                if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
                 if (warp < nJw + nDw) {
                     const int dw = warp - nJw;
                     const int r = t2;
-                    const bool active = r < n;
-                    double2* base = s.D + (active ? r : 0) * pD;
-                    bool done = !active;
+                    double2* base = s.D + (r < n ? r : 0) * pD;
+                    bool done = !(r < n);
                     double mylog = 0.0;
-                    double2 cur = active ? base[0] : make_double2(0.0, 0.0);
-                    for (int k = 0; k < n; ++k) {
+                    double2 cur = done ? make_double2(0.0, 0.0) : base[0];
+                    unsigned wnext;
+                    {
                         const float mag = (float)(fabs(cur.x) + fabs(cur.y));
                         const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
-                        const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                        unsigned gmax = wmax;
+                        wnext = __reduce_max_sync(0xffffffffu, key);
+                        if (nDw > 1 && lane == 0) s.redD[dw] = wnext;
+                    }
+                    for (int k = 0; k < n; ++k) {
+                        unsigned gmax = wnext;
                         if (nDw > 1) {
-                            if (lane == 0) s.redD[(k & 1) * 8 + dw] = wmax;
                             named_bar_sync(2, nDw * 32);
+#pragma unroll
                             for (int w = 0; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
                         } else {
                             __syncwarp();
@@ -646,35 +709,58 @@ sweep_kernel(const SweepParams p) {
                         const double pn = fma(piv.x, piv.x, piv.y * piv.y);
                         if (r == pr) {
                             done = true;
-                            mylog = 0.5 * log(pn);
-                        } else if (!done) {
-                            const double ip = 1.0 / pn;            // l = -cur / piv
-                            const double lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
-                            const double ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
+                            mylog = pn;                            // log taken once, after the loop
+                        }
+                        const bool upd = !done;
+                        double lx = 0.0, ly = 0.0;
+                        if (upd) {
+                            double ip = (double)rcp_approx((float)pn);   // 1/pn: FP32 seed + 2 Newton steps
+                            ip = ip * (2.0 - pn * ip);
+                            ip = ip * (2.0 - pn * ip);               // l = -cur / piv
+                            lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
+                            ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
+                            if (k + 1 < n) {
+                                const double2 pv = prow[k + 1];
+                                double2 v = base[k + 1];
+                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                base[k + 1] = v;
+                                cur = v;
+                            }
+                        }
+                        {
+                            const float mag = (float)(fabs(cur.x) + fabs(cur.y));
+                            const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
+                            wnext = __reduce_max_sync(0xffffffffu, key);
+                            if (nDw > 1 && lane == 0) s.redD[((k + 1) & 1) * 8 + dw] = wnext;
+                        }
+                        if (upd) {
 #pragma unroll 2
-                            for (int j = k + 1; j < n; ++j) {
+                            for (int j = k + 2; j < n; ++j) {
                                 const double2 pv = prow[j];
                                 double2 v = base[j];
                                 v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
                                 v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
                                 base[j] = v;
                             }
-                            if (k + 1 < n) cur = base[k + 1];
                         }
-                        if (nDw == 1) __syncwarp();
                     }
-                    double acc = mylog;
+                    double acc = (r < n) ? 0.5 * log(mylog) : 0.0;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     if (lane == 0) s.lsum[warp] = acc;
                 }
             }
             __syncthreads();
+            if (use_pivot || s.flag[2] == 0) break;
+            use_pivot = true;
+            if (tid == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
+          }
 
             // ---------------- Metropolis accept / reject (MCMC.py:28-33) ------------------------------
             if (tid == 0) {
                 double ldJ = 0.0, ldD = 0.0;
-                for (int w = 0; w < nJw; ++w) ldJ += s.lsum[w];
+                if (use_pivot) { for (int w = 0; w < nJw; ++w) ldJ += s.lsum[8 + w]; } else { ldJ = s.lsum[0]; }
                 for (int w = nJw; w < nJw + nDw; ++w) ldD += s.lsum[w];
                 ldD -= (double)n * log(p.L);                     // D carries L^{-dim/2} per entry (slater.py:17)
                 const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179

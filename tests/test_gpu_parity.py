@@ -123,6 +123,36 @@ def test_logp_general_n_and_weights(cg, oracle):
         assert np.abs(lp - ref).max() < RTOL * max(1.0, np.abs(ref).max()), (n, np.abs(lp - ref).max())
 
 
+def test_jacobian_lu_fallback(cg, cases, oracle, monkeypatch):
+    """The unpivoted 2x2-block LU is the fast path; parameters that take J far from the identity must be caught by
+    its monitors and redone with the partially pivoted LU, and forcing the pivoted path must agree with the fast one."""
+    from oracle import flow as oflow, tables
+    c = cases("n29_rs1")
+    nb = c["ref_logp"].shape[0]
+    logp = cg.make_logp(c["ktable"], c["L"])
+    fast = logp(c["x"][:nb], c["params"], c["state_idx"][:nb])
+    assert logp.fallback_count() == 0                      # trained flow: J = I + O(0.1), never falls back
+    monkeypatch.setenv("CGB_FORCE_PIVOT", "1")
+    piv = logp(c["x"][:nb], c["params"], c["state_idx"][:nb])
+    monkeypatch.delenv("CGB_FORCE_PIVOT")
+    assert np.abs(piv - c["ref_logp"]).max() < RTOL * np.abs(c["ref_logp"]).max()
+    assert np.abs(piv - fast).max() < 1e-4
+    # wild weights: strongly non-identity Jacobian
+    rng = np.random.default_rng(9)
+    kt, _ = tables.ktable(2, 25, (0.25, 0.25))
+    n = 20
+    L = float(np.sqrt(np.pi * n))
+    p = oflow.init_params(2, 16, 16, 2, seed=5, stddev=1.5)
+    x = rng.uniform(0, L, (16, n, 2))
+    si = np.stack([np.sort(rng.choice(kt.shape[0], n, replace=False)) for _ in range(16)]).astype(np.int32)
+    lg = cg.make_logp(kt, L)
+    lp = lg(x, p, si)
+    ref = oracle["logpsi"].logp_batch(x, p, si, kt, L)
+    print("wild weights: %d of 16 evaluations fell back to the pivoted LU" % lg.fallback_count())
+    assert lg.fallback_count() > 0
+    assert np.abs(lp - ref).max() < 1e-4 * np.abs(ref).max(), np.abs(lp - ref).max()
+
+
 # ------------------------------------------------------------------ Metropolis sweep
 def _accept_report(tr_gpu, tr_ref, uniforms):
     acc_g, acc_r = tr_gpu["accept"].astype(bool), tr_ref["accept"].astype(bool)
