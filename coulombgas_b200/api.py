@@ -245,10 +245,8 @@ def mcmc(logp_fn, x_init, key, mc_steps, mc_stddev=0.02, wrap_L=None, return_tra
 
 
 def _all_reduce_sum(vec):
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-    return vec
+    from .dist import psum
+    return psum(vec)
 
 
 def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
