@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Small-shape driver for compute-sanitizer (memcheck / racecheck / synccheck): every kernel, every NW variant once."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import coulombgas_b200 as cg
+from conftest import load_case
+for tag, B in (("n13_rs10", 3), ("n29_rs1", 3), ("n49_rs0.5", 2), ("n57_rs0.25", 2)):
+    c = load_case(tag)
+    logp = cg.make_logp(c["ktable"], c["L"])
+    x, si = c["x"][:B].copy(), c["state_idx"][:B]
+    lp = logp(x, c["params"], si)
+    xs, acc = cg.mcmc(logp.bind(c["params"], si), x, 5, 3, 0.1)
+    os.environ["CGB_FORCE_PIVOT"] = "1"
+    lp2 = logp(x, c["params"], si)
+    del os.environ["CGB_FORCE_PIVOT"]
+    V = cg.potential_energy(x, c["kappa"], c["G"], c["L"], c["rs"])
+    print(tag, lp[:2], lp2[:2], acc, V[:2])
+torch.cuda.synchronize()
+print("sanitize driver done")
