@@ -6,13 +6,19 @@
 //   flow forward (src/flow.py:39-55) -> Slater matrix (src/slater.py:14-17) -> complex LU, and the
 //   analytic Jacobian of the flow (replacing jax.jacfwd, src/logpsi.py:27-28) -> real LU.
 //
-// Thread layout: 4 lanes per particle row ("row i, lane-in-row q"), 8 rows per warp, NW = ceil(n/8) warps.
-// In the two O(n^2) pair passes lane q of row i handles partners j = q, q+4, ...; row sums are 2-stage
-// shuffle butterflies inside the 4-lane group, so no cross-warp reduction buffers are needed.
-// Weights live in shared memory (broadcast LDS.128); per-row contractions Q_i, R_i in registers.
-// LU: one thread per matrix row, rows in shared memory (odd pitch -> conflict-free), pivot search by a
-// single REDUX (integer max of |a| bits with the row id in the low bits) + one named barrier per step;
-// the real 2n x 2n (Jacobian) and complex n x n (Slater) factorisations run concurrently on disjoint warps.
+// Thread layout ("pair layout"): 4 lanes per particle row, 8 rows per warp, NW = ceil(n/8) warps; thread
+// (g = lane/4, q = lane%4) of warp w owns row  i = g*NW + w  (cyclic over warps, so the triangular LU work stays
+// balanced) and the partner / column indices  k = 4*it + q.  This is exactly the accumulator-fragment layout of
+// mma.m16n8k8 with m-tile = the warp's 8 rows x {a=0,1} and n-tile `it` = 4 partners x {d=0,1}: the 2x2 Jacobian
+// block J_ik of a thread's own (row, partner) pair IS its c0..c3.  Hence
+//   * the two O(n^2) pair passes run on FP32 FMA/SFU pipes, row sums by 2-stage quad butterflies;
+//   * the mean-field coupling J_ik += T_i H_k (a (2n x 16)(16 x 2n) product) runs on the tensor cores as
+//     3xTF32 (hi/lo split, FP32-accurate) with zero data movement for A (own registers) and one LDS.128 for B;
+//   * both LU factorisations are REGISTER-resident and use every warp: a thread keeps its row segment
+//     (J: 2x2 blocks, D: complex float64) in registers, only the pivot row travels through a double-buffered
+//     shared-memory line.  J: unpivoted 2x2-block LU, one barrier per step.  D: partially pivoted complex LU
+//     (implicit row exchange), pivot search by REDUX + one smem word per warp, two barriers per step.
+// Weights live in shared memory (broadcast LDS.128); per-row contractions Q_i, R_i, T_i in registers.
 #include "cgb_common.cuh"
 #include "cgb_internal.h"
 
@@ -39,7 +45,7 @@ __global__ void prep_params_kernel(const double* __restrict__ p, float* __restri
 
 // ---------------------------------------------------------------------------------------------------
 // Shared-memory layout.  Everything whose size depends only on the row-slot count N8 = 8*NW sits at
-// compile-time offsets; the two matrices (sizes depend on the run-time n) come last.
+// compile-time offsets; the Jacobian block matrix (size depends on the run-time n) comes last.
 template <int N8>
 struct Lay {
     static constexpr int o_xs = 0;                    // double[2*N8]   current walker
@@ -52,27 +58,27 @@ struct Lay {
     static constexpr int o_k = o_w + 4 * W_TOTAL;     // int2[N8]       integer part of the occupied k rows
     static constexpr int o_pos = o_k + 8 * N8;        // float4[N8]     (cos,sin) of the half angles pi*u
     static constexpr int o_s0 = o_pos + 16 * N8;      // float[N8*16]   sigma0
+    static constexpr int o_Hh = o_s0 + 64 * N8;       // float[N8][2][16] H_k, tf32 "hi" part (aliases double[N8*18] h_i: dead before H is written)
+    static constexpr int o_Hl = o_Hh + 128 * N8;      // float[N8][2][16] H_k, tf32 "lo" part
     // [o_pos, o_red) = pos | sigma0 | H is dead once pass 3 is done: the Slater power tables alias it
-    static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 144 * N8;
-    static constexpr int o_H = o_s0 + 64 * N8;        // float[N8*36] H_k   (aliases double[N8*18] h_i: dead before H is written)
-    static constexpr int o_red = o_H + 144 * N8;      // unsigned[2*8] J pivots, unsigned[2*8] D pivots, int[4] flags
-    static constexpr int o_J = o_red + 160;           // float4[n*pitchB] Jacobian as 2x2 blocks; then max(R|T float[2*N8*36], D double2[n*pitchD])
-    static_assert(o_J % 16 == 0, "alignment");
+    static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 256 * N8;
+    static constexpr int o_red = o_Hl + 128 * N8;     // unsigned[2*8] J pivots (fallback), unsigned[2*8] D pivots, int[4] flags
+    static constexpr int o_pv = o_red + 160;          // pivot line, double-buffered: float4[2][N8+1] (J) / double2[2][N8] (D)
+    static constexpr int o_R = o_pv + 32 * N8 + 32;   // float[N8*36]   R_i rows
+    static constexpr int o_J = o_R + 144 * N8;        // float4[n*pitchB] local Jacobian blocks (pass 2 -> pass 3)
+    static_assert(o_J % 16 == 0 && o_pv % 16 == 0 && o_R % 16 == 0, "alignment");
 };
 __host__ __device__ inline int pitch_B(int n) { return n | 1; }   // float4 blocks per block-row, odd: conflict-free LDS.128
-__host__ __device__ inline int pitch_D(int n) { return n | 1; }                          // odd: conflict-free 16-byte rows
 
 size_t sweep_smem_bytes(int n) {
     const int n8 = 8 * sweep_num_warps(n);
-    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160);
-    const size_t jb = sizeof(float4) * n * pitch_B(n);
-    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(double2) * n * pitch_D(n);
-    return fixed + jb + (rt > dd ? rt : dd);
+    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 8 * n8 + 16 * n8 + 64 * n8 + 256 * n8 + 160 + 32 * n8 + 32 + 144 * n8);
+    return fixed + sizeof(float4) * n * pitch_B(n);
 }
 
 struct Smem {
     float* wts; double* xs; double* xp; float4* pos; double2* us; int2* kint; double2* ptab; double2* dz; float* sig0;
-    double* hbuf; double* hbar; float* Rbuf; float* Tbuf; float* Hbuf; float4* J; double2* D;
+    double* hbuf; double* hbar; float* Rbuf; float* Hh; float* Hl; float4* J; float4* pvJ; double2* pvD;
     unsigned* redJ; unsigned* redD; double* lsum; int* flag;
 };
 
@@ -89,6 +95,30 @@ __device__ __forceinline__ double quad_sum_f64(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
+}
+// ---- tensor-core helpers: m16n8k8 TF32 MMA with FP32 accumulate, and the hi/lo split of "3xTF32"
+// (a*b ~ ah*bh + al*bh + ah*bl, relative error ~2^-21: FP32-grade; a single TF32 product is not accurate
+// enough for log|det J|).
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float4& c, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float4 shfl4(const float4 v, int src) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+__device__ __forceinline__ double2 shfl2d(const double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 // Kahan-compensated accumulation: the sums over partners feed the Slater phases, whose condition number
 // amplifies FP32 summation error past the 1e-5 budget.
@@ -122,12 +152,18 @@ __device__ __forceinline__ PairFeat pair_features(const float4 pi_, const float4
     return f;
 }
 
+
 template <int QQ>
-__device__ __forceinline__ void store_quarter(float* dst, const float (&v)[32]) {
-    // v is [c][d] (16x2); lane QQ stores channels 4QQ..4QQ+3 -> 8 floats
-    float4* d4 = reinterpret_cast<float4*>(dst + 8 * QQ);
-    d4[0] = make_float4(v[8 * QQ + 0], v[8 * QQ + 1], v[8 * QQ + 2], v[8 * QQ + 3]);
-    d4[1] = make_float4(v[8 * QQ + 4], v[8 * QQ + 5], v[8 * QQ + 6], v[8 * QQ + 7]);
+__device__ __forceinline__ void store_quarter_split(float* hh, float* hl, const float (&v)[32]) {
+    // v is [c][d] (16x2); lane QQ stores channels 4QQ..4QQ+3 of row layout [d][c] as tf32 hi / lo parts
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tf32_split(v[2 * (4 * QQ + j) + d], h[j], l[j]);
+        *reinterpret_cast<uint4*>(hh + d * 16 + 4 * QQ) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(hl + d * 16 + 4 * QQ) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -136,26 +172,23 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 2 ? 10 : (NW <= 4 ? 5 : 2)))
 sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = tid >> 2, q = tid & 3;
+    const int q = lane & 3, qbase = lane & ~3;
+    const int row = (lane >> 2) * NW + warp;      // cyclic row ownership (balanced LU)
     const bool rv = row < n;
     const int i = rv ? row : n - 1;
-    constexpr int n8 = 8 * NW;
+    constexpr int n8 = 8 * NW, NIT = 2 * NW;      // NIT = column slots per thread (k = 4*it + q)
     using L_ = Lay<n8>;
-    static_assert(L_::o_J == 16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160, "host size formula");
-    const int N2 = 2 * n, pB = pitch_B(n), pD = pitch_D(n);
+    const int N2 = 2 * n, pB = pitch_B(n);
     Smem s;
     s.xs = (double*)(smem_raw + L_::o_xs); s.xp = (double*)(smem_raw + L_::o_xp); s.lsum = (double*)(smem_raw + L_::o_ls);
     s.hbar = (double*)(smem_raw + L_::o_hb); s.us = (double2*)(smem_raw + L_::o_us); s.dz = (double2*)(smem_raw + L_::o_dz);
     s.wts = (float*)(smem_raw + L_::o_w); s.pos = (float4*)(smem_raw + L_::o_pos); s.kint = (int2*)(smem_raw + L_::o_k); s.ptab = (double2*)(smem_raw + L_::o_pos);
-    s.sig0 = (float*)(smem_raw + L_::o_s0); s.Hbuf = (float*)(smem_raw + L_::o_H); s.hbuf = (double*)(smem_raw + L_::o_H);
+    s.sig0 = (float*)(smem_raw + L_::o_s0); s.Hh = (float*)(smem_raw + L_::o_Hh); s.Hl = (float*)(smem_raw + L_::o_Hl); s.hbuf = (double*)(smem_raw + L_::o_Hh);
     s.redJ = (unsigned*)(smem_raw + L_::o_red); s.redD = s.redJ + 16; s.flag = (int*)(s.redJ + 32);
+    s.pvJ = (float4*)(smem_raw + L_::o_pv); s.pvD = (double2*)(smem_raw + L_::o_pv);
+    s.Rbuf = (float*)(smem_raw + L_::o_R);
     s.J = (float4*)(smem_raw + L_::o_J);     // block (i,k) = (J[2i][2k], J[2i][2k+1], J[2i+1][2k], J[2i+1][2k+1])
-    s.Rbuf = (float*)(s.J + n * pB); s.Tbuf = s.Rbuf + n8 * 36; s.D = (double2*)s.Rbuf;
-    // LU warps: Jacobian on [0,nJw), Slater on [nJw, nJw+nDw); both counts follow from NW = ceil(n/8)
-    constexpr int nJw = (NW + 1) / 2, nDw = NW >= 5 ? 2 : 1;
-    constexpr int nBw = nDw;          // warps of the block-LU fast path (one thread per 2x2 block-row)
-    constexpr int nSw = NW - nJw;     // warps that build the Slater matrix; the first nDw of them factorise it
-    static_assert(nJw + nDw <= NW, "warp roles");
+    constexpr int nJw = (NW + 1) / 2;         // warps of the pivoted fallback LU (one thread per scalar row)
     const float invn = 1.f / (float)n;
     const double invL = 1.0 / p.L;
     const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
@@ -269,6 +302,7 @@ sweep_kernel(const SweepParams p) {
             // ---------------- single-particle stream (flow.py:45,51-55): forward values in float64 ------
             float Q[2][5];       // d z_i / d m0_i
             float s0own[4];      // sigma0_i for channels 4q..4q+3
+            float Tq[2][4];      // T_i[a][4q..4q+3]: this thread's A-fragment slots of the pass-3 MMA
             {
                 const double* __restrict__ P = p.params;        // flat float64 parameters (include/cgb200.h)
                 constexpr int S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
@@ -354,7 +388,7 @@ sweep_kernel(const SweepParams p) {
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int f = 0; f < 5; ++f) Qp[a][f] = 0.f;
-                float Rq[2][4], Tq[2][4];
+                float Rq[2][4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int c = 4 * q + k;
@@ -389,8 +423,6 @@ sweep_kernel(const SweepParams p) {
                 if (rv) {
                     *reinterpret_cast<float4*>(s.Rbuf + row * 36 + 4 * q) = make_float4(Rq[0][0], Rq[0][1], Rq[0][2], Rq[0][3]);
                     *reinterpret_cast<float4*>(s.Rbuf + row * 36 + 16 + 4 * q) = make_float4(Rq[1][0], Rq[1][1], Rq[1][2], Rq[1][3]);
-                    *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 4 * q) = make_float4(Tq[0][0], Tq[0][1], Tq[0][2], Tq[0][3]);
-                    *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 16 + 4 * q) = make_float4(Tq[1][0], Tq[1][1], Tq[1][2], Tq[1][3]);
                 }
             }
             __syncthreads();     // h_i (aliased by H) and the R/T rows are complete before the pair passes touch them
@@ -492,154 +524,180 @@ sweep_kernel(const SweepParams p) {
                     Hacc[2 * c + 1] = (Hacc[2 * c + 1] - s0c * oy) * invn;
                 }
                 if (rv) {
-                    float* hd = s.Hbuf + row * 36;
-                    if (q == 0) store_quarter<0>(hd, Hacc);
-                    else if (q == 1) store_quarter<1>(hd, Hacc);
-                    else if (q == 2) store_quarter<2>(hd, Hacc);
-                    else store_quarter<3>(hd, Hacc);
+                    float* hh = s.Hh + row * 32;
+                    float* hl = s.Hl + row * 32;
+                    if (q == 0) store_quarter_split<0>(hh, hl, Hacc);
+                    else if (q == 1) store_quarter_split<1>(hh, hl, Hacc);
+                    else if (q == 2) store_quarter_split<2>(hh, hl, Hacc);
+                    else store_quarter_split<3>(hh, hl, Hacc);
                 }
             }
             __syncthreads();
 
-            // ---------------- pass 3: mean-field coupling  J_ik += T_i H_k, then the diagonal block ----
+            // ---------------- pass 3 (tensor cores): mean-field coupling  J_ik += T_i H_k, then the diagonal block --
+            // m-tile = this warp's 8 rows x {a}, n-tile `it` = partners 4it..4it+3 x {d}, K = 16 channels in two
+            // k-steps; K-slot (ks, t) <-> channel 4t+2ks, (ks, t+4) <-> channel 4t+2ks+1, so the A fragments are this
+            // thread's own T_i[a][4q..4q+3] and the B fragments one LDS.128 of H_k[d][4q..4q+3].  3xTF32.
+            float4 Jr[NIT];                          // this thread's Jacobian blocks J_{row, 4it+q}
             {
-                float T[2][16];
+                uint32_t Ah[2][4], Al[2][4];
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+                for (int ks = 0; ks < 2; ++ks) {
+                    tf32_split(Tq[0][2 * ks], Ah[ks][0], Al[ks][0]);
+                    tf32_split(Tq[1][2 * ks], Ah[ks][1], Al[ks][1]);
+                    tf32_split(Tq[0][2 * ks + 1], Ah[ks][2], Al[ks][2]);
+                    tf32_split(Tq[1][2 * ks + 1], Ah[ks][3], Al[ks][3]);
+                }
+                rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
+                const int hoff = (lane >> 2) * 16 + 4 * q;     // ((g>>1)*2 + (g&1))*16 + 4q  within the n-tile's 4 partners
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 v = *reinterpret_cast<const float4*>(s.Tbuf + i * 36 + a * 16 + 4 * c4);
-                        T[a][4 * c4 + 0] = v.x; T[a][4 * c4 + 1] = v.y; T[a][4 * c4 + 2] = v.z; T[a][4 * c4 + 3] = v.w;
-                    }
-                for (int it = 0; it < iters; ++it) {
-                    const int k = q + 4 * it;
-                    if (k < n && k != i) {
-                        float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
-#pragma unroll
-                        for (int c2 = 0; c2 < 8; ++c2) {
-                            const float4 hv = *reinterpret_cast<const float4*>(s.Hbuf + k * 36 + 4 * c2);   // (c,x),(c,y),(c+1,x),(c+1,y)
-                            t00 = fmaf(T[0][2 * c2], hv.x, fmaf(T[0][2 * c2 + 1], hv.z, t00));
-                            t01 = fmaf(T[0][2 * c2], hv.y, fmaf(T[0][2 * c2 + 1], hv.w, t01));
-                            t10 = fmaf(T[1][2 * c2], hv.x, fmaf(T[1][2 * c2 + 1], hv.z, t10));
-                            t11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, t11));
-                        }
-                        if (rv) {
-                            float4 v = s.J[row * pB + k];
-                            v.x += t00; v.y += t01; v.z += t10; v.w += t11;
-                            s.J[row * pB + k] = v;
-                        }
-                        rs[0] += t00; rs[1] += t01; rs[2] += t10; rs[3] += t11;
-                    }
+                for (int it = 0; it < NIT; ++it) {
+                    const int k = 4 * it + q;
+                    const bool valid = rv && k < n && k != row;
+                    float4 acc = s.J[i * pB + (k < n ? k : n - 1)];
+                    const uint4 bh = *reinterpret_cast<const uint4*>(s.Hh + it * 128 + hoff);
+                    const uint4 bl = *reinterpret_cast<const uint4*>(s.Hl + it * 128 + hoff);
+                    mma_tf32(acc, Al[0], bh.x, bh.y);
+                    mma_tf32(acc, Ah[0], bl.x, bl.y);
+                    mma_tf32(acc, Al[1], bh.z, bh.w);
+                    mma_tf32(acc, Ah[1], bl.z, bl.w);
+                    mma_tf32(acc, Ah[0], bh.x, bh.y);
+                    mma_tf32(acc, Ah[1], bh.z, bh.w);
+                    if (!valid) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rs[0] += acc.x; rs[1] += acc.y; rs[2] += acc.z; rs[3] += acc.w;
+                    Jr[it] = acc;
                 }
 #pragma unroll
                 for (int t = 0; t < 4; ++t) rs[t] = quad_sum(rs[t]);
-                if (rv && q == 0) {          // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
-                    s.J[row * pB + row] = make_float4(1.f - rs[0], -rs[1], -rs[2], 1.f - rs[3]);
+                // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
+                const float4 dg = make_float4(1.f - rs[0], -rs[1], -rs[2], 1.f - rs[3]);
+#pragma unroll
+                for (int it = 0; it < NIT; ++it)
+                    if (4 * it + q == row) Jr[it] = dg;
+            }
+            if ((p.out_jac && step == 0) || use_pivot) {     // rare paths need the assembled J in shared memory
+                __syncthreads();
+                if (rv) {
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it)
+                        if (4 * it + q < n) s.J[row * pB + 4 * it + q] = Jr[it];
+                }
+                __syncthreads();
+                if (p.out_jac && step == 0) {
+                    float* oj = p.out_jac + (size_t)b * N2 * N2;
+                    for (int t = tid; t < N2 * N2; t += NW * 32) {
+                        const int rr = t / N2, cc = t - rr * N2;
+                        oj[t] = reinterpret_cast<const float*>(s.J)[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)];
+                    }
                 }
             }
-            __syncthreads();
-            if (p.out_jac && step == 0) {
-                float* oj = p.out_jac + (size_t)b * N2 * N2;
-                for (int t = tid; t < N2 * N2; t += NW * 32) {
-                    const int rr = t / N2, cc = t - rr * N2;
-                    oj[t] = reinterpret_cast<const float*>(s.J)[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)];
+
+            // ---------------- Jacobian LU:  log|det J| --------------------------------------------------------
+            // J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU on the register-
+            // resident blocks: at step k the quad of row k publishes its row (and -P_kk^{-1}) to the pivot line,
+            // one barrier, every later row updates its own registers.  log|det J| = sum_k log|det P_kk|.
+            // Multipliers and pivot determinants are monitored; if they leave the safe range the whole evaluation
+            // is redone with the partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
+            float lacc = 0.f;                         // log2|det P_kk| of the pivots this thread owned
+            if (!use_pivot) {
+                bool bad = false;
+#pragma unroll
+                for (int kb = 0; kb < NIT; ++kb) {
+#pragma unroll 1
+                    for (int kq = 0; kq < 4; ++kq) {
+                        const int k = 4 * kb + kq;
+                        if (k >= n) break;
+                        float4* line = s.pvJ + (k & 1) * (n8 + 1);
+                        const float4 a = shfl4(Jr[kb], qbase + kq);     // column-k block of the own row (P_kk on row k)
+                        if (row == k) {
+                            const float det = a.x * a.w - a.y * a.z;
+                            const float idet = rcp_approx(det);
+                            if (q == kq) {
+                                lacc += lg2_approx(fabsf(det));
+                                bad |= !(fabsf(det) > 0.05f);            // also catches NaN
+                            }
+                            if (q == 0) line[n8] = make_float4(-a.w * idet, a.y * idet, a.z * idet, -a.x * idet);   // -P^{-1}
+#pragma unroll
+                            for (int it = kb; it < NIT; ++it) line[4 * it + q] = Jr[it];
+                        }
+                        __syncthreads();
+                        if (rv && row > k) {
+                            const float4 m = line[n8];
+                            const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
+                            const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
+                            bad |= (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
+#pragma unroll
+                            for (int it = kb; it < NIT; ++it) {
+                                if (it > kb || q > kq) {
+                                    const float4 pv = line[4 * it + q];
+                                    float4 v = Jr[it];
+                                    v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
+                                    v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
+                                    v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
+                                    v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
+                                    Jr[it] = v;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (bad) s.flag[2] = 1;
+                __syncthreads();
+                if (s.flag[2]) {                     // block-uniform: redo this evaluation with the pivoted LU
+                    use_pivot = true;
+                    if (tid == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
+                    continue;
+                }
+            } else {
+                // ---- fallback: scalar LU with partial pivoting on the blocked shared-memory copy, one thread per row.
+                // |a| bits with the row id in the low 7 bits -> one REDUX per warp; per-warp maxima exchanged
+                // through a double-buffered slot, one named barrier per elimination step.
+                if (warp < nJw) {
+                    const int r = tid;
+                    float* Jf = reinterpret_cast<float*>(s.J);
+                    auto el = [&](int rr, int cc) -> float& { return Jf[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)]; };
+                    bool done = !(r < N2);
+                    float mylog = 0.f;
+                    for (int k = 0; k < N2; ++k) {
+                        const float cur = done ? 0.f : el(r, k);
+                        const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
+                        const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                        if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
+                        if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
+                        unsigned gmax = s.redJ[(k & 1) * 8];
+#pragma unroll
+                        for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
+                        const int pr = (int)(gmax & 0x7Fu);
+                        const float piv = el(pr, k);
+                        if (r == pr) {
+                            done = true;
+                            mylog = lg2_approx(fabsf(piv));
+                        } else if (!done) {
+                            const float l = -cur / piv;
+                            for (int j = k + 1; j < N2; ++j) el(r, j) = fmaf(l, el(pr, j), el(r, j));
+                        }
+                        if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
+                    }
+                    lacc = mylog;
                 }
                 __syncthreads();
             }
 
-            // ---------------- LU phase: real 2n x 2n FP32 Jacobian || complex n x n FP64 Slater matrix ---------
-            // Jacobian: J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU, one
-            // thread per block-row (2 rows), blocks in shared memory: log|det J| = sum_k log|det P_kk|.  Half the
-            // sequential depth of a scalar LU, no pivot search, no cross-warp exchange.  Multipliers and pivot
-            // determinants are monitored; if they leave the safe range the whole evaluation is redone with the
-            // partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
-            if (!use_pivot && warp < nBw) {
-                const int bi = tid;
-                const bool act = bi < n;
-                float4* brow = s.J + (act ? bi : 0) * pB;
-                float lacc = 0.f;
-                bool bad = false;
-                for (int k = 0; k < n; ++k) {
-                    if (nBw > 1) named_bar_sync(1, nBw * 32); else __syncwarp();
-                    const float4* prow = s.J + k * pB;
-                    const float4 pk = prow[k];                              // pivot block (broadcast)
-                    const float det = pk.x * pk.w - pk.y * pk.z;
-                    const float idet = rcp_approx(det);
-                    lacc += lg2_approx(fabsf(det));                          // identical in every lane
-                    bad |= !(fabsf(det) > 0.05f);                            // also catches NaN
-                    if (act && bi > k) {
-                        const float4 a = brow[k];
-                        // -L = -A_ik P_kk^{-1},  P^{-1} = [[w,-y],[-z,x]] / det
-                        const float l00 = (a.y * pk.z - a.x * pk.w) * idet, l01 = (a.x * pk.y - a.y * pk.x) * idet;
-                        const float l10 = (a.w * pk.z - a.z * pk.w) * idet, l11 = (a.z * pk.y - a.w * pk.x) * idet;
-                        bad |= (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
-#pragma unroll 4
-                        for (int j = k + 1; j < n; ++j) {
-                            const float4 qv = prow[j];
-                            float4 v = brow[j];
-                            v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
-                            v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
-                            v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
-                            v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
-                            brow[j] = v;
-                        }
-                    }
-                }
-                if (__any_sync(0xffffffffu, bad) && lane == 0) s.flag[2] = 1;
-                if (tid == 0) s.lsum[0] = (double)lacc * 0.693147180559945309417;
-            } else if (use_pivot && warp < nJw) {
-                // ---- fallback: scalar LU with partial pivoting on the blocked storage, one thread per row.
-                // |a| bits with the row id in the low 7 bits -> one REDUX per warp; per-warp maxima exchanged
-                // through a double-buffered slot, one named barrier per elimination step.
-                const int r = tid;
-                float* Jf = reinterpret_cast<float*>(s.J);
-                auto el = [&](int rr, int cc) -> float& { return Jf[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)]; };
-                bool done = !(r < N2);
-                float mylog = 0.f;
-                for (int k = 0; k < N2; ++k) {
-                    const float cur = done ? 0.f : el(r, k);
-                    const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
-                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                    if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
-                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
-                    unsigned gmax = s.redJ[(k & 1) * 8];
-#pragma unroll
-                    for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
-                    const int pr = (int)(gmax & 0x7Fu);
-                    const float piv = el(pr, k);
-                    if (r == pr) {
-                        done = true;
-                        mylog = lg2_approx(fabsf(piv));
-                    } else if (!done) {
-                        const float l = -cur / piv;
-                        for (int j = k + 1; j < N2; ++j) el(r, j) = fmaf(l, el(pr, j), el(r, j));
-                    }
-                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
-                }
-                double acc = (double)mylog;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) s.lsum[8 + warp] = acc * 0.693147180559945309417;
-            }
-            if (warp >= NW - nSw) {
-                // ---- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + (dz - mean dz)/L
-                // (src/slater.py:14-17; the twist and the common displacement are pure row/column phases
-                // and drop out of |det|).  All warps >= nJw build entries; the first nDw of them factorise.
-                constexpr int nb = nSw * 32;
-                const int t2 = tid - nJw * 32;
+            // ---------------- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + dz/L ----------------
+            // (src/slater.py:14-17; the twist and any common displacement are pure row/column phases and drop out of
+            // |det|).  Thread (row, q) builds and keeps the entries of columns j = 4it+q in registers.
+            double2 Dr[NIT];
+            {
                 const int mmax = s.flag[1];                      // max |m| over this walker's occupied orbitals
-                if (mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes) {
+                const bool tables = mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes;
+                if (tables) {
                     // power tables  X_r^m = e^{2 pi i m w_rx},  Y_r^m,  m = 1..mmax  (one sincospi per coordinate)
-                    for (int c = t2; c < 2 * n; c += nb) {
-                        const int rr = c >> 1, comp = c & 1;
-                        double mean = 0.0;
-                        for (int t = 0; t < n; ++t) mean += reinterpret_cast<const double*>(s.dz)[2 * t + comp];
-                        mean /= (double)n;
-                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[c] - mean, invL,
-                                              reinterpret_cast<const double*>(s.us)[c]);
+                    if (tid < N2) {
+                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[tid], invL,
+                                              reinterpret_cast<const double*>(s.us)[tid]);
                         double sn, cs;
                         sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
-                        double2* tb = s.ptab + (size_t)c * mmax;   // [row][comp][m-1]
+                        double2* tb = s.ptab + (size_t)tid * mmax;   // [row][comp][m-1]
                         double2 pw = make_double2(cs, sn);
                         tb[0] = pw;
                         for (int m = 1; m < mmax; ++m) {
@@ -647,121 +705,129 @@ sweep_kernel(const SweepParams p) {
                             tb[m] = pw;
                         }
                     }
-                    if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
-                    for (int j = t2 >> 5; j < n; j += nb / 32) {
-                        const int rr = t2 & 31;
-                        const int2 mk = s.kint[j];
+                    __syncthreads();
 #pragma unroll
-                        for (int half = 0; half < (NW > 4 ? 2 : 1); ++half) {
-                            const int r2 = rr + 32 * half;
-                            if (r2 < n) {
-                                const int ax = abs(mk.x), ay = abs(mk.y);
-                                double2 X = make_double2(1.0, 0.0), Y = make_double2(1.0, 0.0);
-                                if (ax) { X = s.ptab[(size_t)(2 * r2) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
-                                if (ay) { Y = s.ptab[(size_t)(2 * r2 + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
-                                s.D[r2 * pD + j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
-                            }
+                    for (int it = 0; it < NIT; ++it) {
+                        const int j = 4 * it + q;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (rv && j < n) {
+                            const int2 mk = s.kint[j];
+                            const int ax = abs(mk.x), ay = abs(mk.y);
+                            double2 X = make_double2(1.0, 0.0), Y = make_double2(1.0, 0.0);
+                            if (ax) { X = s.ptab[(size_t)(2 * row) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
+                            if (ay) { Y = s.ptab[(size_t)(2 * row + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
+                            v = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
                         }
+                        Dr[it] = v;
                     }
                 } else {
-                    double mx = 0.0, my = 0.0;
-                    for (int t = 0; t < n; ++t) { const double2 v = s.dz[t]; mx += v.x; my += v.y; }
-                    mx /= (double)n; my /= (double)n;
-                    for (int idx = t2; idx < n * n; idx += nb) {
-                        const int rr = idx / n, j = idx - rr * n;
-                        const double2 uu = s.us[rr], dd = s.dz[rr];
-                        const double wx = fma(dd.x - mx, invL, uu.x), wy = fma(dd.y - my, invL, uu.y);
-                        const int2 mk = s.kint[j];
-                        double ph = fma((double)mk.x, wx, (double)mk.y * wy);
-                        ph -= rint(ph);
-                        double sn, cs;
-                        sincospi(2.0 * ph, &sn, &cs);
-                        s.D[rr * pD + j] = make_double2(cs, sn);
-                    }
-                }
-                if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
-                if (warp < nJw + nDw) {
-                    const int dw = warp - nJw;
-                    const int r = t2;
-                    double2* base = s.D + (r < n ? r : 0) * pD;
-                    bool done = !(r < n);
-                    double mylog = 0.0;
-                    double2 cur = done ? make_double2(0.0, 0.0) : base[0];
-                    unsigned wnext;
-                    {
-                        const float mag = (float)(fabs(cur.x) + fabs(cur.y));
-                        const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
-                        wnext = __reduce_max_sync(0xffffffffu, key);
-                        if (nDw > 1 && lane == 0) s.redD[dw] = wnext;
-                    }
-                    for (int k = 0; k < n; ++k) {
-                        unsigned gmax = wnext;
-                        if (nDw > 1) {
-                            named_bar_sync(2, nDw * 32);
+                    const double2 uu = s.us[i], dd = s.dz[i];
+                    const double wx = fma(dd.x, invL, uu.x), wy = fma(dd.y, invL, uu.y);
 #pragma unroll
-                            for (int w = 0; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
-                        } else {
-                            __syncwarp();
+                    for (int it = 0; it < NIT; ++it) {
+                        const int j = 4 * it + q;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (rv && j < n) {
+                            const int2 mk = s.kint[j];
+                            double ph = fma((double)mk.x, wx, (double)mk.y * wy);
+                            ph -= rint(ph);
+                            double sn, cs;
+                            sincospi(2.0 * ph, &sn, &cs);
+                            v = make_double2(cs, sn);
                         }
-                        const int pr = (int)(gmax & 0x7Fu);
-                        const double2* prow = s.D + pr * pD;
-                        const double2 piv = prow[k];
-                        const double pn = fma(piv.x, piv.x, piv.y * piv.y);
-                        if (r == pr) {
-                            done = true;
-                            mylog = pn;                            // log taken once, after the loop
-                        }
-                        const bool upd = !done;
-                        double lx = 0.0, ly = 0.0;
-                        if (upd) {
-                            double ip = (double)rcp_approx((float)pn);   // 1/pn: FP32 seed + 2 Newton steps
-                            ip = ip * (2.0 - pn * ip);
-                            ip = ip * (2.0 - pn * ip);               // l = -cur / piv
-                            lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
-                            ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
-                            if (k + 1 < n) {
-                                const double2 pv = prow[k + 1];
-                                double2 v = base[k + 1];
-                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
-                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                                base[k + 1] = v;
-                                cur = v;
-                            }
-                        }
-                        {
-                            const float mag = (float)(fabs(cur.x) + fabs(cur.y));
-                            const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
-                            wnext = __reduce_max_sync(0xffffffffu, key);
-                            if (nDw > 1 && lane == 0) s.redD[((k + 1) & 1) * 8 + dw] = wnext;
-                        }
-                        if (upd) {
-#pragma unroll 2
-                            for (int j = k + 2; j < n; ++j) {
-                                const double2 pv = prow[j];
-                                double2 v = base[j];
-                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
-                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                                base[j] = v;
-                            }
-                        }
+                        Dr[it] = v;
                     }
-                    double acc = (r < n) ? 0.5 * log(mylog) : 0.0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (lane == 0) s.lsum[warp] = acc;
                 }
             }
+            // ---------------- Slater LU: partially pivoted (implicit row exchange), register-resident rows ----------
+            // step k: [barrier A] per-warp maxima of column k -> pivot row pr; its quad publishes the row scaled by
+            // 1/pivot; [barrier B] every unfinished row eliminates column k in its registers, then posts its candidate
+            // for column k+1 (REDUX).  log|det D| = sum over pivots of log|pivot|.
+            bool singular = false;                    // a zero pivot column: det D = 0 (block-uniform)
+            double mypn = 1.0;                        // |pivot|^2 of the pivot this thread owned (log taken once, at the end)
+            {
+                bool done = !rv;
+                auto pkey = [&](const double2 e) -> unsigned {
+                    const float mag = (float)(fabs(e.x) + fabs(e.y));
+                    return (__float_as_uint(mag) & ~0x7Fu) | (unsigned)row;
+                };
+                {
+                    const unsigned key = (!done && q == 0) ? pkey(Dr[0]) : 0u;
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0) s.redD[warp] = wmax;
+                }
+#pragma unroll
+                for (int kb = 0; kb < NIT; ++kb) {
+#pragma unroll 1
+                    for (int kq = 0; kq < 4; ++kq) {
+                        const int k = 4 * kb + kq;
+                        if (k >= n) break;
+                        double2* line = s.pvD + (k & 1) * n8;
+                        __syncthreads();                                   // A: candidates of column k are posted
+                        unsigned gmax = s.redD[(k & 1) * 8];
+#pragma unroll
+                        for (int w = 1; w < NW; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                        const int pr = (int)(gmax & 0x7Fu);
+                        singular |= (gmax >> 7) == 0u;
+                        const double2 c = shfl2d(Dr[kb], qbase + kq);      // column-k entry of the own row (the pivot on row pr)
+                        if (row == pr && !done) {
+                            const double pn = fma(c.x, c.x, c.y * c.y);
+                            double ip = (double)rcp_approx((float)pn);     // 1/pn: FP32 seed + 2 Newton steps
+                            ip = ip * (2.0 - pn * ip);
+                            ip = ip * (2.0 - pn * ip);
+                            const double ix = c.x * ip, iy = -c.y * ip;    // 1/pivot
+#pragma unroll
+                            for (int it = kb; it < NIT; ++it) {
+                                const double2 v = Dr[it];
+                                line[4 * it + q] = make_double2(v.x * ix - v.y * iy, v.x * iy + v.y * ix);
+                            }
+                            if (q == kq) mypn = pn;
+                            done = true;
+                        }
+                        __syncthreads();                                   // B: the scaled pivot row is in the line
+                        if (!done) {
+                            const double lx = -c.x, ly = -c.y;
+#pragma unroll
+                            for (int it = kb; it < NIT; ++it) {
+                                if (it > kb || q > kq) {
+                                    const double2 pv = line[4 * it + q];
+                                    double2 v = Dr[it];
+                                    v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                    v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                    Dr[it] = v;
+                                }
+                            }
+                        }
+                        if (k + 1 < n) {                                   // candidate for column k+1
+                            double2 e = Dr[kb];
+                            if (kb + 1 < NIT) { if (kq == 3) e = Dr[kb + 1]; }
+                            const unsigned key = (!done && q == ((kq + 1) & 3)) ? pkey(e) : 0u;
+                            const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                            if (lane == 0) s.redD[((k + 1) & 1) * 8 + warp] = wmax;
+                        }
+                    }
+                }
+            }
+            // ---------------- block reduction of the two log-determinants -----------------------------------------
+            {
+                double aJ = (double)lacc * 0.693147180559945309417;
+                double aD = (mypn != 1.0) ? 0.5 * log(mypn) : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    aJ += __shfl_xor_sync(0xffffffffu, aJ, o);
+                    aD += __shfl_xor_sync(0xffffffffu, aD, o);
+                }
+                if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
+                if (lane == 0) { s.lsum[warp] = aD; s.lsum[8 + warp] = aJ; }
+            }
             __syncthreads();
-            if (use_pivot || s.flag[2] == 0) break;
-            use_pivot = true;
-            if (tid == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
+            break;
           }
 
             // ---------------- Metropolis accept / reject (MCMC.py:28-33) ------------------------------
             if (tid == 0) {
                 double ldJ = 0.0, ldD = 0.0;
-                if (use_pivot) { for (int w = 0; w < nJw; ++w) ldJ += s.lsum[8 + w]; } else { ldJ = s.lsum[0]; }
-                for (int w = nJw; w < nJw + nDw; ++w) ldD += s.lsum[w];
+                for (int w = 0; w < NW; ++w) { ldD += s.lsum[w]; ldJ += s.lsum[8 + w]; }
                 ldD -= (double)n * log(p.L);                     // D carries L^{-dim/2} per entry (slater.py:17)
                 const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179
                 int acc = 1;
