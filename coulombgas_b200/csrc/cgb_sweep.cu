@@ -7,8 +7,7 @@
 //   analytic Jacobian of the flow (replacing jax.jacfwd, src/logpsi.py:27-28) -> real LU.
 //
 // Thread layout ("pair layout"): 4 lanes per particle row, 8 rows per warp, NW = ceil(n/8) warps; thread
-// (g = lane/4, q = lane%4) of warp w owns row  i = g*NW + w  (cyclic over warps, so the triangular LU work stays
-// balanced) and the partner / column indices  k = 4*it + q.  This is exactly the accumulator-fragment layout of
+// (g = lane/4, q = lane%4) of warp w owns row  i = 8w + g  and the partner / column indices  k = 4*it + q.  This is exactly the accumulator-fragment layout of
 // mma.m16n8k8 with m-tile = the warp's 8 rows x {a=0,1} and n-tile `it` = 4 partners x {d=0,1}: the 2x2 Jacobian
 // block J_ik of a thread's own (row, partner) pair IS its c0..c3.  Hence
 //   * the two O(n^2) pair passes run on FP32 FMA/SFU pipes, row sums by 2-stage quad butterflies;
@@ -63,8 +62,8 @@ struct Lay {
     // [o_pos, o_red) = pos | sigma0 | H is dead once pass 3 is done: the Slater power tables alias it
     static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 256 * N8;
     static constexpr int o_red = o_Hl + 128 * N8;     // unsigned[2*8] J pivots (fallback), unsigned[2*8] D pivots, int[4] flags
-    static constexpr int o_pv = o_red + 160;          // pivot line, double-buffered: float4[2][N8+1] (J) / double2[2][N8] (D)
-    static constexpr int o_R = o_pv + 32 * N8 + 32;   // float[N8*36]   R_i rows
+    static constexpr int o_pv = o_red + 160;          // pivot lines, double-buffered: float4[2][N8+1] (J) / double2[2][NW][N8] + candidate slots (D)
+    static constexpr int o_R = o_pv + 4 * N8 * N8 + 512;   // float[N8*36]   R_i rows
     static constexpr int o_J = o_R + 144 * N8;        // float4[n*pitchB] local Jacobian blocks (pass 2 -> pass 3)
     static_assert(o_J % 16 == 0 && o_pv % 16 == 0 && o_R % 16 == 0, "alignment");
 };
@@ -72,7 +71,7 @@ __host__ __device__ inline int pitch_B(int n) { return n | 1; }   // float4 bloc
 
 size_t sweep_smem_bytes(int n) {
     const int n8 = 8 * sweep_num_warps(n);
-    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 8 * n8 + 16 * n8 + 64 * n8 + 256 * n8 + 160 + 32 * n8 + 32 + 144 * n8);
+    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 8 * n8 + 16 * n8 + 64 * n8 + 256 * n8 + 160 + 4 * n8 * n8 + 512 + 144 * n8);
     return fixed + sizeof(float4) * n * pitch_B(n);
 }
 
@@ -128,12 +127,44 @@ __device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
     comp = (t - sum) - y;
     sum = t;
 }
-// float64 softplus (forward value) + FP32 logistic sigmoid (Jacobian side) of a float64 pre-activation
+// float64 softplus (forward value) + FP32 logistic sigmoid (Jacobian side) of a float64 pre-activation.
+// softplus(x) = max(x,0) + log1p(t), t = exp(-|x|).  Accuracy target 1e-11 relative (the Slater phases need the
+// backflow displacement to ~1e-9), far below libm's cost: exp by range reduction + degree-10 Taylor,
+// log1p(t) = 2 atanh(t/(2+t)) by a degree-10 series in u^2 <= 1/9 with a Newton-refined FP32 reciprocal.
 __device__ __forceinline__ void softplus_sigmoid_f64(double pre, double& sp, float& sg) {
-    const double e = exp(-fabs(pre));
-    sp = fmax(pre, 0.0) + log1p(e);
-    const float ef = (float)e, r = rcp_approx(1.f + ef);
-    sg = pre >= 0.0 ? r : ef * r;
+    double y = fmax(-fabs(pre) * 1.4426950408889634074, -1000.0);
+    const double kf = rint(y);
+    const double f = (y - kf) * 0.69314718055994530942;          // |f| <= 0.3466
+    double pz = 2.7557319223985891e-07;                            // 1/10!
+    pz = fma(pz, f, 2.7557319223985893e-06);
+    pz = fma(pz, f, 2.4801587301587302e-05);
+    pz = fma(pz, f, 1.9841269841269841e-04);
+    pz = fma(pz, f, 1.3888888888888889e-03);
+    pz = fma(pz, f, 8.3333333333333332e-03);
+    pz = fma(pz, f, 4.1666666666666664e-02);
+    pz = fma(pz, f, 1.6666666666666666e-01);
+    pz = fma(pz, f, 0.5);
+    pz = fma(pz, f, 1.0);
+    pz = fma(pz, f, 1.0);
+    const double t = pz * __hiloint2double(((int)kf + 1023) << 20, 0);    // exp(-|pre|) in (0,1]
+    const double d = 2.0 + t;
+    const double r0 = (double)rcp_approx((float)d);
+    const double r = fma(r0, fma(-d, r0, 1.0), r0);               // 1/d to ~1e-14
+    const double u = t * r, w = u * u;
+    double a = 4.7619047619047616e-02;                             // 1/21
+    a = fma(a, w, 5.2631578947368418e-02);
+    a = fma(a, w, 5.8823529411764705e-02);
+    a = fma(a, w, 6.6666666666666666e-02);
+    a = fma(a, w, 7.6923076923076927e-02);
+    a = fma(a, w, 9.0909090909090912e-02);
+    a = fma(a, w, 1.1111111111111111e-01);
+    a = fma(a, w, 1.4285714285714285e-01);
+    a = fma(a, w, 0.2);
+    a = fma(a, w, 3.3333333333333331e-01);
+    a = fma(a, w, 1.0);
+    sp = fmax(pre, 0.0) + 2.0 * u * a;
+    const float ef = (float)t, rr = rcp_approx(1.f + ef);
+    sg = pre >= 0.0 ? rr : ef * rr;
 }
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
@@ -173,7 +204,7 @@ sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = lane & 3, qbase = lane & ~3;
-    const int row = (lane >> 2) * NW + warp;      // cyclic row ownership (balanced LU)
+    const int row = 8 * warp + (lane >> 2);       // contiguous rows per warp: finished warps drop out of the J-LU
     const bool rv = row < n;
     const int i = rv ? row : n - 1;
     constexpr int n8 = 8 * NW, NIT = 2 * NW;      // NIT = column slots per thread (k = 4*it + q)
@@ -594,51 +625,67 @@ sweep_kernel(const SweepParams p) {
 
             // ---------------- Jacobian LU:  log|det J| --------------------------------------------------------
             // J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU on the register-
-            // resident blocks: at step k the quad of row k publishes its row (and -P_kk^{-1}) to the pivot line,
-            // one barrier, every later row updates its own registers.  log|det J| = sum_k log|det P_kk|.
+            // resident blocks.  Step k: every row below k eliminates block column k with the published pivot line
+            // k (and -P_kk^{-1}); row k+1 -- whose blocks are final after this update -- inverts its diagonal block
+            // and publishes line k+1 in the same step (look-ahead: the reciprocal chain overlaps the remaining
+            // updates), so there is ONE barrier per step.  Rows are contiguous per warp: a warp whose rows are all
+            // finished only keeps the barrier count.  log|det J| = sum_k log|det P_kk|.
             // Multipliers and pivot determinants are monitored; if they leave the safe range the whole evaluation
             // is redone with the partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
             float lacc = 0.f;                         // log2|det P_kk| of the pivots this thread owned
             if (!use_pivot) {
                 bool bad = false;
+                auto publish_inv = [&](const float4 pk, float4* line) {     // by the one thread that owns P_kk
+                    const float det = pk.x * pk.w - pk.y * pk.z;
+                    const float idet = rcp_approx(det);
+                    lacc += lg2_approx(fabsf(det));
+                    bad |= !(fabsf(det) > 0.05f);                            // also catches NaN
+                    line[n8] = make_float4(-pk.w * idet, pk.y * idet, pk.z * idet, -pk.x * idet);   // -P^{-1}
+                };
+                if (row == 0) {
+                    if (q == 0) publish_inv(Jr[0], s.pvJ);
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) s.pvJ[4 * it + q] = Jr[it];
+                }
+                __syncthreads();
 #pragma unroll
                 for (int kb = 0; kb < NIT; ++kb) {
 #pragma unroll 1
                     for (int kq = 0; kq < 4; ++kq) {
                         const int k = 4 * kb + kq;
                         if (k >= n) break;
-                        float4* line = s.pvJ + (k & 1) * (n8 + 1);
-                        const float4 a = shfl4(Jr[kb], qbase + kq);     // column-k block of the own row (P_kk on row k)
-                        if (row == k) {
-                            const float det = a.x * a.w - a.y * a.z;
-                            const float idet = rcp_approx(det);
-                            if (q == kq) {
-                                lacc += lg2_approx(fabsf(det));
-                                bad |= !(fabsf(det) > 0.05f);            // also catches NaN
-                            }
-                            if (q == 0) line[n8] = make_float4(-a.w * idet, a.y * idet, a.z * idet, -a.x * idet);   // -P^{-1}
+                        if (8 * warp + 7 > k) {                             // warp-uniform: some row of this warp is below the pivot
+                            const float4* line = s.pvJ + (k & 1) * (n8 + 1);
+                            float4* nline = s.pvJ + ((k + 1) & 1) * (n8 + 1);
+                            const float4 a = shfl4(Jr[kb], qbase + kq);     // column-k block of the own row
+                            if (rv && row > k) {
+                                const float4 m = line[n8];
+                                const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
+                                const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
+                                bad |= fmaxf(fmaxf(fabsf(l00), fabsf(l01)), fmaxf(fabsf(l10), fabsf(l11))) > 2.f;
+                                const bool nxt = row == k + 1;
 #pragma unroll
-                            for (int it = kb; it < NIT; ++it) line[4 * it + q] = Jr[it];
-                        }
-                        __syncthreads();
-                        if (rv && row > k) {
-                            const float4 m = line[n8];
-                            const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
-                            const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
-                            bad |= (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
+                                for (int it = kb; it < NIT; ++it) {
+                                    if (it > kb || q > kq) {
+                                        const float4 pv = line[4 * it + q];
+                                        float4 v = Jr[it];
+                                        v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
+                                        v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
+                                        v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
+                                        v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
+                                        Jr[it] = v;
+                                    }
+                                    // the next pivot block P_{k+1,k+1} is final now: invert it early
+                                    if (it == kb && kq < 3 && nxt && q == kq + 1) publish_inv(Jr[it], nline);
+                                    if (it == kb + 1 && kq == 3 && nxt && q == 0) publish_inv(Jr[it], nline);
+                                }
+                                if (nxt) {
 #pragma unroll
-                            for (int it = kb; it < NIT; ++it) {
-                                if (it > kb || q > kq) {
-                                    const float4 pv = line[4 * it + q];
-                                    float4 v = Jr[it];
-                                    v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
-                                    v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
-                                    v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
-                                    v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
-                                    Jr[it] = v;
+                                    for (int it = kb; it < NIT; ++it) nline[4 * it + q] = Jr[it];
                                 }
                             }
                         }
+                        __syncthreads();
                     }
                 }
                 if (bad) s.flag[2] = 1;
@@ -740,71 +787,97 @@ sweep_kernel(const SweepParams p) {
                 }
             }
             // ---------------- Slater LU: partially pivoted (implicit row exchange), register-resident rows ----------
-            // step k: [barrier A] per-warp maxima of column k -> pivot row pr; its quad publishes the row scaled by
-            // 1/pivot; [barrier B] every unfinished row eliminates column k in its registers, then posts its candidate
-            // for column k+1 (REDUX).  log|det D| = sum over pivots of log|pivot|.
+            // ONE barrier per step.  After eliminating column k every unfinished row offers its column-(k+1) entry;
+            // a REDUX picks the warp's best candidate, whose quad speculatively publishes its (already final) row
+            // into the warp's line together with 1/candidate -- the reciprocal chain overlaps the remaining updates.
+            // After the barrier all threads take the best of the NW warp candidates: pivot row, its line, its inverse.
+            // log|det D| = sum over pivots of log|pivot|.
             bool singular = false;                    // a zero pivot column: det D = 0 (block-uniform)
             double mypn = 1.0;                        // |pivot|^2 of the pivot this thread owned (log taken once, at the end)
             {
                 bool done = !rv;
-                auto pkey = [&](const double2 e) -> unsigned {
+                double2* lines = s.pvD;                                            // [2][NW][n8]
+                double2* sinv = reinterpret_cast<double2*>(smem_raw + L_::o_pv + 4 * n8 * n8);   // [2][8] 1/candidate
+                double* spn = reinterpret_cast<double*>(sinv + 16);                // [2][8] |candidate|^2
+                unsigned* skey = reinterpret_cast<unsigned*>(spn + 16);            // [2][8] candidate keys
+                // offer the column-`col` entry e (held by lane qe of each row) as this warp's pivot candidate
+                auto offer = [&](const double2 e, const int qe, const int par, bool& win) -> unsigned {
                     const float mag = (float)(fabs(e.x) + fabs(e.y));
-                    return (__float_as_uint(mag) & ~0x7Fu) | (unsigned)row;
+                    const unsigned key = (!done && q == qe) ? ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)row) : 0u;
+                    const unsigned wk = __reduce_max_sync(0xffffffffu, key);
+                    win = !done && row == (int)(wk & 0x7Fu) && (wk >> 7) != 0u;
+                    if (win && q == qe) {
+                        const double pn = fma(e.x, e.x, e.y * e.y);
+                        double ip = (double)rcp_approx((float)pn);                 // 1/pn: FP32 seed + 2 Newton steps
+                        ip = ip * (2.0 - pn * ip);
+                        ip = ip * (2.0 - pn * ip);
+                        sinv[par * 8 + warp] = make_double2(e.x * ip, -e.y * ip);
+                        spn[par * 8 + warp] = pn;
+                    }
+                    return wk;
                 };
                 {
-                    const unsigned key = (!done && q == 0) ? pkey(Dr[0]) : 0u;
-                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                    if (lane == 0) s.redD[warp] = wmax;
+                    bool win;
+                    const unsigned wk = offer(Dr[0], 0, 0, win);
+                    if (win) {
+#pragma unroll
+                        for (int it = 0; it < NIT; ++it) lines[warp * n8 + 4 * it + q] = Dr[it];
+                    }
+                    if (lane == 0) skey[warp] = wk;
                 }
+                __syncthreads();
 #pragma unroll
                 for (int kb = 0; kb < NIT; ++kb) {
 #pragma unroll 1
                     for (int kq = 0; kq < 4; ++kq) {
                         const int k = 4 * kb + kq;
                         if (k >= n) break;
-                        double2* line = s.pvD + (k & 1) * n8;
-                        __syncthreads();                                   // A: candidates of column k are posted
-                        unsigned gmax = s.redD[(k & 1) * 8];
+                        const int par = k & 1;
+                        unsigned gmax = skey[par * 8];
+                        int wbest = 0;
 #pragma unroll
-                        for (int w = 1; w < NW; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                        for (int w = 1; w < NW; ++w) {
+                            const unsigned kw = skey[par * 8 + w];
+                            if (kw > gmax) { gmax = kw; wbest = w; }
+                        }
                         const int pr = (int)(gmax & 0x7Fu);
                         singular |= (gmax >> 7) == 0u;
                         const double2 c = shfl2d(Dr[kb], qbase + kq);      // column-k entry of the own row (the pivot on row pr)
                         if (row == pr && !done) {
-                            const double pn = fma(c.x, c.x, c.y * c.y);
-                            double ip = (double)rcp_approx((float)pn);     // 1/pn: FP32 seed + 2 Newton steps
-                            ip = ip * (2.0 - pn * ip);
-                            ip = ip * (2.0 - pn * ip);
-                            const double ix = c.x * ip, iy = -c.y * ip;    // 1/pivot
-#pragma unroll
-                            for (int it = kb; it < NIT; ++it) {
-                                const double2 v = Dr[it];
-                                line[4 * it + q] = make_double2(v.x * ix - v.y * iy, v.x * iy + v.y * ix);
-                            }
-                            if (q == kq) mypn = pn;
+                            if (q == kq) mypn = spn[par * 8 + wbest];
                             done = true;
                         }
-                        __syncthreads();                                   // B: the scaled pivot row is in the line
+                        const double2* line = lines + (par * NW + wbest) * n8;
+                        double lx = 0.0, ly = 0.0;
                         if (!done) {
-                            const double lx = -c.x, ly = -c.y;
+                            const double2 iv = sinv[par * 8 + wbest];
+                            lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
+                            ly = -(c.x * iv.y + c.y * iv.x);
+                        }
+                        bool win = false;
+                        unsigned wk = 0u;
 #pragma unroll
-                            for (int it = kb; it < NIT; ++it) {
-                                if (it > kb || q > kq) {
-                                    const double2 pv = line[4 * it + q];
-                                    double2 v = Dr[it];
-                                    v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
-                                    v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                                    Dr[it] = v;
-                                }
+                        for (int it = kb; it < NIT; ++it) {
+                            if (!done && (it > kb || q > kq)) {
+                                const double2 pv = line[4 * it + q];
+                                double2 v = Dr[it];
+                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                Dr[it] = v;
                             }
+                            // column k+1 is final now: offer it as the next pivot candidate (look-ahead)
+                            if (it == kb && kq < 3 && k + 1 < n) wk = offer(Dr[it], kq + 1, par ^ 1, win);
+                            if (it == kb + 1 && kq == 3 && k + 1 < n) wk = offer(Dr[it], 0, par ^ 1, win);
                         }
-                        if (k + 1 < n) {                                   // candidate for column k+1
-                            double2 e = Dr[kb];
-                            if (kb + 1 < NIT) { if (kq == 3) e = Dr[kb + 1]; }
-                            const unsigned key = (!done && q == ((kq + 1) & 3)) ? pkey(e) : 0u;
-                            const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                            if (lane == 0) s.redD[((k + 1) & 1) * 8 + warp] = wmax;
+                        if (k + 1 < n) {
+                            if (win) {
+                                double2* nl = lines + ((par ^ 1) * NW + warp) * n8;
+#pragma unroll
+                                for (int it = kb; it < NIT; ++it) nl[4 * it + q] = Dr[it];
+                            }
+                            if (lane == 0) skey[(par ^ 1) * 8 + warp] = wk;
                         }
+                        __syncthreads();
                     }
                 }
             }
