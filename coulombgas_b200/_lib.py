@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcgb200.so")
+LIB_PATH = os.environ.get("CGB_LIB") or os.path.join(_HERE, "libcgb200.so")   # CGB_LIB: developer A/B builds only
 
 NPARAMS = 1074
 MAX_N = 64

@@ -115,10 +115,12 @@ class Logp:
 
     def workspace(self, B, n):
         d = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
-        if d not in self._ws:
-            nbytes = ctypes.c_size_t()
-            check(lib.cgb_logp_workspace_bytes(B, n, ctypes.byref(nbytes)), "cgb_logp_workspace_bytes")
+        nbytes = ctypes.c_size_t()
+        check(lib.cgb_logp_workspace_bytes(B, n, ctypes.byref(nbytes)), "cgb_logp_workspace_bytes")
+        if d not in self._ws or self._ws[d].numel() < nbytes.value:      # grows with the batch (per-walker scheduler state)
+            fb = self.fallback_count()
             self._ws[d] = torch.zeros(nbytes.value, dtype=torch.uint8, device=_dev())
+            self._ws[d][4096:4104].view(torch.int64).fill_(fb)            # the fallback counter is cumulative
         return self._ws[d]
 
     def fallback_count(self):

@@ -64,13 +64,12 @@ int cgb_ewald_prepare_host(const int64_t* G, int nG, double kappa, float* items_
     return CGB_OK;
 }
 
-static size_t wpack_bytes() { return ((sizeof(float) * W_TOTAL) + 255) & ~size_t(255); }
-static size_t workspace_total() { return wpack_bytes() + 256; }   // + cumulative pivot-fallback counter (uint64)
+static size_t workspace_total(int B) { return ws_total_bytes(B); }   // layout: cgb_internal.h (WS_*)
 
 int cgb_logp_workspace_bytes(int B, int n, size_t* bytes) {
     if (!bytes || B < 0) return CGB_E_BADARG;
     if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
-    *bytes = workspace_total();
+    *bytes = workspace_total(B);
     return CGB_OK;
 }
 int cgb_mcmc_workspace_bytes(int B, int n, size_t* bytes) { return cgb_logp_workspace_bytes(B, n, bytes); }
@@ -85,12 +84,10 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
         return CGB_E_BADARG;
     if ((noise == nullptr) != (uniforms == nullptr)) return CGB_E_BADARG;
     if (n < 2 || n > CGB_MAX_N) return CGB_E_UNSUPPORTED;
-    if (!workspace || workspace_bytes < workspace_total() || ((uintptr_t)workspace & 15)) return CGB_E_WORKSPACE;
+    if (!workspace || workspace_bytes < workspace_total(B) || ((uintptr_t)workspace & 15)) return CGB_E_WORKSPACE;
     if ((uintptr_t)params & 15) return CGB_E_BADARG;            // float64 parameters are read as 16-byte pairs
     if (B == 0) return CGB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_prep_params(params, (float*)workspace, st);
-    if (rc) return rc;
     SweepParams p;
     p.x = x; p.x_out = x_out; p.state_idx = state_idx; p.ktable = ktable; p.M = M;
     p.tw0 = twist[0]; p.tw1 = twist[1]; p.wpack = (const float*)workspace; p.params = params;
@@ -99,7 +96,26 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     p.out_acc_trace = acc_trace; p.out_logp_trace = logp_trace; p.out_parts = out_parts; p.out_jac = out_jac;
     const char* fp = getenv("CGB_FORCE_PIVOT");                    // debug knob: exercise the pivoted fallback LU
     p.force_pivot = (fp && fp[0] == '1') ? 1 : 0;
-    p.fallback_counter = (unsigned long long*)((char*)workspace + wpack_bytes());
+    char* ws = (char*)workspace;
+    p.fallback_counter = (unsigned long long*)(ws + WS_CTR);
+    p.qctr = (unsigned long long*)(ws + WS_CTR + 64);
+    p.qcap = ws_qcap(B);
+    p.queue = (unsigned long long*)(ws + WS_DYN);
+    {
+        size_t o = WS_DYN + ws_round(8 * (size_t)p.qcap);
+        p.done = (int*)(ws + o); o += ws_round(sizeof(int) * (size_t)B);
+        p.ws_logp = (double*)(ws + o); o += ws_round(sizeof(double) * (size_t)B);
+        p.ws_nacc = (int*)(ws + o);
+    }
+    // kernel choice: the warp-per-walker kernel (cgb_wsweep.cu) for the instantiated n <= 32 shapes, the
+    // CTA-per-walker kernel (cgb_sweep.cu) otherwise.  CGB_SWEEP_KERNEL=cta|warp overrides (debug / A-B timing).
+    const char* kk = getenv("CGB_SWEEP_KERNEL");
+    bool use_warp = wsweep_supported(n);
+    if (kk && kk[0] == 'c') use_warp = false;
+    if (kk && kk[0] == 'w' && !wsweep_supported(n)) return CGB_E_UNSUPPORTED;
+    if (use_warp) return launch_wsweep(p, ws + WS_WCONST, st);
+    int rc = launch_prep_params(params, (float*)workspace, st);
+    if (rc) return rc;
     return launch_sweep(p, st);
 }
 

@@ -45,12 +45,36 @@ struct SweepParams {
     float* out_jac;           // (B,2n,2n) or null
     int force_pivot;          // debug: always use the pivoted scalar LU for the Jacobian
     unsigned long long* fallback_counter;   // evaluations redone with the pivoted LU (in the workspace)
+    // ---- warp-per-walker kernel only (cgb_wsweep.cu): per-call scheduler state in the caller's workspace
+    unsigned long long* qctr;     // [0] queue head, [1] queue tail, [2] spin diagnostics (initialised per call)
+    unsigned long long* queue;    // (qcap) ready-queue slots
+    unsigned qcap;                // power of two >= 2*B
+    int* done;                    // (B) steps completed per walker
+    double* ws_logp;              // (B) current log p per walker
+    int* ws_nacc;                 // (B) accepted moves so far
 };
+
+// workspace layout (bytes); the B-dependent arrays start at WS_DYN
+enum : size_t {
+    WS_WPACK = 0,           // W_TOTAL floats (CTA-per-walker kernel)
+    WS_CTR = 4096,          // +0: pivot-fallback counter (u64, cumulative); +64: queue head, tail, spin diagnostics (3 x u64)
+    WS_WCONST = 4352,       // staging copy of the constant-bank weight block (warp-per-walker kernel)
+    WS_DYN = 4352 + 11264
+};
+inline unsigned ws_qcap(int B) { unsigned c = 64; while (c < 2u * (unsigned)(B > 0 ? B : 1)) c <<= 1; return c; }
+inline size_t ws_round(size_t b) { return (b + 255) & ~size_t(255); }
+inline size_t ws_total_bytes(int B) {
+    return WS_DYN + ws_round(8 * (size_t)ws_qcap(B)) + ws_round(sizeof(int) * (size_t)B) + ws_round(sizeof(double) * (size_t)B) +
+           ws_round(sizeof(int) * (size_t)B);
+}
 
 inline int sweep_num_warps(int n) { int w = (n + 7) / 8; return w < 2 ? 2 : w; }
 size_t sweep_smem_bytes(int n);
 int launch_sweep(const SweepParams& p, cudaStream_t st);
 int launch_prep_params(const double* params, float* wpack, cudaStream_t st);
+// warp-per-walker sweep (n <= 32, instantiated shapes only): returns CGB_E_UNSUPPORTED when n has no instance
+bool wsweep_supported(int n);
+int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st);
 
 struct EwaldParams {
     const double* x; int B, n; double L, rs, kappa;

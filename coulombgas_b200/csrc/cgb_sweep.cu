@@ -6,18 +6,13 @@
 //   flow forward (src/flow.py:39-55) -> Slater matrix (src/slater.py:14-17) -> complex LU, and the
 //   analytic Jacobian of the flow (replacing jax.jacfwd, src/logpsi.py:27-28) -> real LU.
 //
-// Thread layout ("pair layout"): 4 lanes per particle row, 8 rows per warp, NW = ceil(n/8) warps; thread
-// (g = lane/4, q = lane%4) of warp w owns row  i = 8w + g  and the partner / column indices  k = 4*it + q.  This is exactly the accumulator-fragment layout of
-// mma.m16n8k8 with m-tile = the warp's 8 rows x {a=0,1} and n-tile `it` = 4 partners x {d=0,1}: the 2x2 Jacobian
-// block J_ik of a thread's own (row, partner) pair IS its c0..c3.  Hence
-//   * the two O(n^2) pair passes run on FP32 FMA/SFU pipes, row sums by 2-stage quad butterflies;
-//   * the mean-field coupling J_ik += T_i H_k (a (2n x 16)(16 x 2n) product) runs on the tensor cores as
-//     3xTF32 (hi/lo split, FP32-accurate) with zero data movement for A (own registers) and one LDS.128 for B;
-//   * both LU factorisations are REGISTER-resident and use every warp: a thread keeps its row segment
-//     (J: 2x2 blocks, D: complex float64) in registers, only the pivot row travels through a double-buffered
-//     shared-memory line.  J: unpivoted 2x2-block LU, one barrier per step.  D: partially pivoted complex LU
-//     (implicit row exchange), pivot search by REDUX + one smem word per warp, two barriers per step.
-// Weights live in shared memory (broadcast LDS.128); per-row contractions Q_i, R_i, T_i in registers.
+// Thread layout: 4 lanes per particle row ("row i, lane-in-row q"), 8 rows per warp, NW = ceil(n/8) warps.
+// In the two O(n^2) pair passes lane q of row i handles partners j = q, q+4, ...; row sums are 2-stage
+// shuffle butterflies inside the 4-lane group, so no cross-warp reduction buffers are needed.
+// Weights live in shared memory (broadcast LDS.128); per-row contractions Q_i, R_i in registers.
+// LU: one thread per matrix row, rows in shared memory (odd pitch -> conflict-free), pivot search by a
+// single REDUX (integer max of |a| bits with the row id in the low bits) + one named barrier per step;
+// the real 2n x 2n (Jacobian) and complex n x n (Slater) factorisations run concurrently on disjoint warps.
 #include "cgb_common.cuh"
 #include "cgb_internal.h"
 
@@ -44,7 +39,7 @@ __global__ void prep_params_kernel(const double* __restrict__ p, float* __restri
 
 // ---------------------------------------------------------------------------------------------------
 // Shared-memory layout.  Everything whose size depends only on the row-slot count N8 = 8*NW sits at
-// compile-time offsets; the Jacobian block matrix (size depends on the run-time n) comes last.
+// compile-time offsets; the two matrices (sizes depend on the run-time n) come last.
 template <int N8>
 struct Lay {
     static constexpr int o_xs = 0;                    // double[2*N8]   current walker
@@ -57,27 +52,27 @@ struct Lay {
     static constexpr int o_k = o_w + 4 * W_TOTAL;     // int2[N8]       integer part of the occupied k rows
     static constexpr int o_pos = o_k + 8 * N8;        // float4[N8]     (cos,sin) of the half angles pi*u
     static constexpr int o_s0 = o_pos + 16 * N8;      // float[N8*16]   sigma0
-    static constexpr int o_Hh = o_s0 + 64 * N8;       // float[N8][2][16] H_k, tf32 "hi" part (aliases double[N8*18] h_i: dead before H is written)
-    static constexpr int o_Hl = o_Hh + 128 * N8;      // float[N8][2][16] H_k, tf32 "lo" part
     // [o_pos, o_red) = pos | sigma0 | H is dead once pass 3 is done: the Slater power tables alias it
-    static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 256 * N8;
-    static constexpr int o_red = o_Hl + 128 * N8;     // unsigned[2*8] J pivots (fallback), unsigned[2*8] D pivots, int[4] flags
-    static constexpr int o_pv = o_red + 160;          // pivot lines, double-buffered: float4[2][N8+1] (J) / double2[2][NW][N8] + candidate slots (D)
-    static constexpr int o_R = o_pv + 4 * N8 * N8 + 512;   // float[N8*36]   R_i rows
-    static constexpr int o_J = o_R + 144 * N8;        // float4[n*pitchB] local Jacobian blocks (pass 2 -> pass 3)
-    static_assert(o_J % 16 == 0 && o_pv % 16 == 0 && o_R % 16 == 0, "alignment");
+    static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 144 * N8;
+    static constexpr int o_H = o_s0 + 64 * N8;        // float[N8*36] H_k   (aliases double[N8*18] h_i: dead before H is written)
+    static constexpr int o_red = o_H + 144 * N8;      // unsigned[2*8] J pivots, unsigned[2*8] D pivots, int[4] flags
+    static constexpr int o_J = o_red + 160;           // float4[n*pitchB] Jacobian as 2x2 blocks; then max(R|T float[2*N8*36], D double2[n*pitchD])
+    static_assert(o_J % 16 == 0, "alignment");
 };
 __host__ __device__ inline int pitch_B(int n) { return n | 1; }   // float4 blocks per block-row, odd: conflict-free LDS.128
+__host__ __device__ inline int pitch_D(int n) { return n | 1; }                          // odd: conflict-free 16-byte rows
 
 size_t sweep_smem_bytes(int n) {
     const int n8 = 8 * sweep_num_warps(n);
-    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 8 * n8 + 16 * n8 + 64 * n8 + 256 * n8 + 160 + 4 * n8 * n8 + 512 + 144 * n8);
-    return fixed + sizeof(float4) * n * pitch_B(n);
+    const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160);
+    const size_t jb = sizeof(float4) * n * pitch_B(n);
+    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(double2) * n * pitch_D(n);
+    return fixed + jb + (rt > dd ? rt : dd);
 }
 
 struct Smem {
     float* wts; double* xs; double* xp; float4* pos; double2* us; int2* kint; double2* ptab; double2* dz; float* sig0;
-    double* hbuf; double* hbar; float* Rbuf; float* Hh; float* Hl; float4* J; float4* pvJ; double2* pvD;
+    double* hbuf; double* hbar; float* Rbuf; float* Tbuf; float* Hbuf; float4* J; double2* D;
     unsigned* redJ; unsigned* redD; double* lsum; int* flag;
 };
 
@@ -95,30 +90,6 @@ __device__ __forceinline__ double quad_sum_f64(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
 }
-// ---- tensor-core helpers: m16n8k8 TF32 MMA with FP32 accumulate, and the hi/lo split of "3xTF32"
-// (a*b ~ ah*bh + al*bh + ah*bl, relative error ~2^-21: FP32-grade; a single TF32 product is not accurate
-// enough for log|det J|).
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-    uint32_t y;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float4& c, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float4 shfl4(const float4 v, int src) {
-    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
-                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
-}
-__device__ __forceinline__ double2 shfl2d(const double2 v, int src) {
-    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-}
 // Kahan-compensated accumulation: the sums over partners feed the Slater phases, whose condition number
 // amplifies FP32 summation error past the 1e-5 budget.
 __device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
@@ -127,44 +98,12 @@ __device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
     comp = (t - sum) - y;
     sum = t;
 }
-// float64 softplus (forward value) + FP32 logistic sigmoid (Jacobian side) of a float64 pre-activation.
-// softplus(x) = max(x,0) + log1p(t), t = exp(-|x|).  Accuracy target 1e-11 relative (the Slater phases need the
-// backflow displacement to ~1e-9), far below libm's cost: exp by range reduction + degree-10 Taylor,
-// log1p(t) = 2 atanh(t/(2+t)) by a degree-10 series in u^2 <= 1/9 with a Newton-refined FP32 reciprocal.
+// float64 softplus (forward value) + FP32 logistic sigmoid (Jacobian side) of a float64 pre-activation
 __device__ __forceinline__ void softplus_sigmoid_f64(double pre, double& sp, float& sg) {
-    double y = fmax(-fabs(pre) * 1.4426950408889634074, -1000.0);
-    const double kf = rint(y);
-    const double f = (y - kf) * 0.69314718055994530942;          // |f| <= 0.3466
-    double pz = 2.7557319223985891e-07;                            // 1/10!
-    pz = fma(pz, f, 2.7557319223985893e-06);
-    pz = fma(pz, f, 2.4801587301587302e-05);
-    pz = fma(pz, f, 1.9841269841269841e-04);
-    pz = fma(pz, f, 1.3888888888888889e-03);
-    pz = fma(pz, f, 8.3333333333333332e-03);
-    pz = fma(pz, f, 4.1666666666666664e-02);
-    pz = fma(pz, f, 1.6666666666666666e-01);
-    pz = fma(pz, f, 0.5);
-    pz = fma(pz, f, 1.0);
-    pz = fma(pz, f, 1.0);
-    const double t = pz * __hiloint2double(((int)kf + 1023) << 20, 0);    // exp(-|pre|) in (0,1]
-    const double d = 2.0 + t;
-    const double r0 = (double)rcp_approx((float)d);
-    const double r = fma(r0, fma(-d, r0, 1.0), r0);               // 1/d to ~1e-14
-    const double u = t * r, w = u * u;
-    double a = 4.7619047619047616e-02;                             // 1/21
-    a = fma(a, w, 5.2631578947368418e-02);
-    a = fma(a, w, 5.8823529411764705e-02);
-    a = fma(a, w, 6.6666666666666666e-02);
-    a = fma(a, w, 7.6923076923076927e-02);
-    a = fma(a, w, 9.0909090909090912e-02);
-    a = fma(a, w, 1.1111111111111111e-01);
-    a = fma(a, w, 1.4285714285714285e-01);
-    a = fma(a, w, 0.2);
-    a = fma(a, w, 3.3333333333333331e-01);
-    a = fma(a, w, 1.0);
-    sp = fmax(pre, 0.0) + 2.0 * u * a;
-    const float ef = (float)t, rr = rcp_approx(1.f + ef);
-    sg = pre >= 0.0 ? rr : ef * rr;
+    const double e = exp(-fabs(pre));
+    sp = fmax(pre, 0.0) + log1p(e);
+    const float ef = (float)e, r = rcp_approx(1.f + ef);
+    sg = pre >= 0.0 ? r : ef * r;
 }
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
@@ -183,18 +122,12 @@ __device__ __forceinline__ PairFeat pair_features(const float4 pi_, const float4
     return f;
 }
 
-
 template <int QQ>
-__device__ __forceinline__ void store_quarter_split(float* hh, float* hl, const float (&v)[32]) {
-    // v is [c][d] (16x2); lane QQ stores channels 4QQ..4QQ+3 of row layout [d][c] as tf32 hi / lo parts
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tf32_split(v[2 * (4 * QQ + j) + d], h[j], l[j]);
-        *reinterpret_cast<uint4*>(hh + d * 16 + 4 * QQ) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(hl + d * 16 + 4 * QQ) = make_uint4(l[0], l[1], l[2], l[3]);
-    }
+__device__ __forceinline__ void store_quarter(float* dst, const float (&v)[32]) {
+    // v is [c][d] (16x2); lane QQ stores channels 4QQ..4QQ+3 -> 8 floats
+    float4* d4 = reinterpret_cast<float4*>(dst + 8 * QQ);
+    d4[0] = make_float4(v[8 * QQ + 0], v[8 * QQ + 1], v[8 * QQ + 2], v[8 * QQ + 3]);
+    d4[1] = make_float4(v[8 * QQ + 4], v[8 * QQ + 5], v[8 * QQ + 6], v[8 * QQ + 7]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -203,23 +136,26 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 2 ? 10 : (NW <= 4 ? 5 : 2)))
 sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = lane & 3, qbase = lane & ~3;
-    const int row = 8 * warp + (lane >> 2);       // contiguous rows per warp: finished warps drop out of the J-LU
+    const int row = tid >> 2, q = tid & 3;
     const bool rv = row < n;
     const int i = rv ? row : n - 1;
-    constexpr int n8 = 8 * NW, NIT = 2 * NW;      // NIT = column slots per thread (k = 4*it + q)
+    constexpr int n8 = 8 * NW;
     using L_ = Lay<n8>;
-    const int N2 = 2 * n, pB = pitch_B(n);
+    static_assert(L_::o_J == 16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160, "host size formula");
+    const int N2 = 2 * n, pB = pitch_B(n), pD = pitch_D(n);
     Smem s;
     s.xs = (double*)(smem_raw + L_::o_xs); s.xp = (double*)(smem_raw + L_::o_xp); s.lsum = (double*)(smem_raw + L_::o_ls);
     s.hbar = (double*)(smem_raw + L_::o_hb); s.us = (double2*)(smem_raw + L_::o_us); s.dz = (double2*)(smem_raw + L_::o_dz);
     s.wts = (float*)(smem_raw + L_::o_w); s.pos = (float4*)(smem_raw + L_::o_pos); s.kint = (int2*)(smem_raw + L_::o_k); s.ptab = (double2*)(smem_raw + L_::o_pos);
-    s.sig0 = (float*)(smem_raw + L_::o_s0); s.Hh = (float*)(smem_raw + L_::o_Hh); s.Hl = (float*)(smem_raw + L_::o_Hl); s.hbuf = (double*)(smem_raw + L_::o_Hh);
+    s.sig0 = (float*)(smem_raw + L_::o_s0); s.Hbuf = (float*)(smem_raw + L_::o_H); s.hbuf = (double*)(smem_raw + L_::o_H);
     s.redJ = (unsigned*)(smem_raw + L_::o_red); s.redD = s.redJ + 16; s.flag = (int*)(s.redJ + 32);
-    s.pvJ = (float4*)(smem_raw + L_::o_pv); s.pvD = (double2*)(smem_raw + L_::o_pv);
-    s.Rbuf = (float*)(smem_raw + L_::o_R);
     s.J = (float4*)(smem_raw + L_::o_J);     // block (i,k) = (J[2i][2k], J[2i][2k+1], J[2i+1][2k], J[2i+1][2k+1])
-    constexpr int nJw = (NW + 1) / 2;         // warps of the pivoted fallback LU (one thread per scalar row)
+    s.Rbuf = (float*)(s.J + n * pB); s.Tbuf = s.Rbuf + n8 * 36; s.D = (double2*)s.Rbuf;
+    // LU warps: Jacobian on [0,nJw), Slater on [nJw, nJw+nDw); both counts follow from NW = ceil(n/8)
+    constexpr int nJw = (NW + 1) / 2, nDw = NW >= 5 ? 2 : 1;
+    constexpr int nBw = nDw;          // warps of the block-LU fast path (one thread per 2x2 block-row)
+    constexpr int nSw = NW - nJw;     // warps that build the Slater matrix; the first nDw of them factorise it
+    static_assert(nJw + nDw <= NW, "warp roles");
     const float invn = 1.f / (float)n;
     const double invL = 1.0 / p.L;
     const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
@@ -333,7 +269,6 @@ sweep_kernel(const SweepParams p) {
             // ---------------- single-particle stream (flow.py:45,51-55): forward values in float64 ------
             float Q[2][5];       // d z_i / d m0_i
             float s0own[4];      // sigma0_i for channels 4q..4q+3
-            float Tq[2][4];      // T_i[a][4q..4q+3]: this thread's A-fragment slots of the pass-3 MMA
             {
                 const double* __restrict__ P = p.params;        // flat float64 parameters (include/cgb200.h)
                 constexpr int S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
@@ -419,7 +354,7 @@ sweep_kernel(const SweepParams p) {
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int f = 0; f < 5; ++f) Qp[a][f] = 0.f;
-                float Rq[2][4];
+                float Rq[2][4], Tq[2][4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int c = 4 * q + k;
@@ -454,6 +389,8 @@ sweep_kernel(const SweepParams p) {
                 if (rv) {
                     *reinterpret_cast<float4*>(s.Rbuf + row * 36 + 4 * q) = make_float4(Rq[0][0], Rq[0][1], Rq[0][2], Rq[0][3]);
                     *reinterpret_cast<float4*>(s.Rbuf + row * 36 + 16 + 4 * q) = make_float4(Rq[1][0], Rq[1][1], Rq[1][2], Rq[1][3]);
+                    *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 4 * q) = make_float4(Tq[0][0], Tq[0][1], Tq[0][2], Tq[0][3]);
+                    *reinterpret_cast<float4*>(s.Tbuf + row * 36 + 16 + 4 * q) = make_float4(Tq[1][0], Tq[1][1], Tq[1][2], Tq[1][3]);
                 }
             }
             __syncthreads();     // h_i (aliased by H) and the R/T rows are complete before the pair passes touch them
@@ -555,196 +492,154 @@ sweep_kernel(const SweepParams p) {
                     Hacc[2 * c + 1] = (Hacc[2 * c + 1] - s0c * oy) * invn;
                 }
                 if (rv) {
-                    float* hh = s.Hh + row * 32;
-                    float* hl = s.Hl + row * 32;
-                    if (q == 0) store_quarter_split<0>(hh, hl, Hacc);
-                    else if (q == 1) store_quarter_split<1>(hh, hl, Hacc);
-                    else if (q == 2) store_quarter_split<2>(hh, hl, Hacc);
-                    else store_quarter_split<3>(hh, hl, Hacc);
+                    float* hd = s.Hbuf + row * 36;
+                    if (q == 0) store_quarter<0>(hd, Hacc);
+                    else if (q == 1) store_quarter<1>(hd, Hacc);
+                    else if (q == 2) store_quarter<2>(hd, Hacc);
+                    else store_quarter<3>(hd, Hacc);
                 }
             }
             __syncthreads();
 
-            // ---------------- pass 3 (tensor cores): mean-field coupling  J_ik += T_i H_k, then the diagonal block --
-            // m-tile = this warp's 8 rows x {a}, n-tile `it` = partners 4it..4it+3 x {d}, K = 16 channels in two
-            // k-steps; K-slot (ks, t) <-> channel 4t+2ks, (ks, t+4) <-> channel 4t+2ks+1, so the A fragments are this
-            // thread's own T_i[a][4q..4q+3] and the B fragments one LDS.128 of H_k[d][4q..4q+3].  3xTF32.
-            float4 Jr[NIT];                          // this thread's Jacobian blocks J_{row, 4it+q}
+            // ---------------- pass 3: mean-field coupling  J_ik += T_i H_k, then the diagonal block ----
             {
-                uint32_t Ah[2][4], Al[2][4];
+                float T[2][16];
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    tf32_split(Tq[0][2 * ks], Ah[ks][0], Al[ks][0]);
-                    tf32_split(Tq[1][2 * ks], Ah[ks][1], Al[ks][1]);
-                    tf32_split(Tq[0][2 * ks + 1], Ah[ks][2], Al[ks][2]);
-                    tf32_split(Tq[1][2 * ks + 1], Ah[ks][3], Al[ks][3]);
-                }
-                rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
-                const int hoff = (lane >> 2) * 16 + 4 * q;     // ((g>>1)*2 + (g&1))*16 + 4q  within the n-tile's 4 partners
+                for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int it = 0; it < NIT; ++it) {
-                    const int k = 4 * it + q;
-                    const bool valid = rv && k < n && k != row;
-                    float4 acc = s.J[i * pB + (k < n ? k : n - 1)];
-                    const uint4 bh = *reinterpret_cast<const uint4*>(s.Hh + it * 128 + hoff);
-                    const uint4 bl = *reinterpret_cast<const uint4*>(s.Hl + it * 128 + hoff);
-                    mma_tf32(acc, Al[0], bh.x, bh.y);
-                    mma_tf32(acc, Ah[0], bl.x, bl.y);
-                    mma_tf32(acc, Al[1], bh.z, bh.w);
-                    mma_tf32(acc, Ah[1], bl.z, bl.w);
-                    mma_tf32(acc, Ah[0], bh.x, bh.y);
-                    mma_tf32(acc, Ah[1], bh.z, bh.w);
-                    if (!valid) acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    rs[0] += acc.x; rs[1] += acc.y; rs[2] += acc.z; rs[3] += acc.w;
-                    Jr[it] = acc;
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 v = *reinterpret_cast<const float4*>(s.Tbuf + i * 36 + a * 16 + 4 * c4);
+                        T[a][4 * c4 + 0] = v.x; T[a][4 * c4 + 1] = v.y; T[a][4 * c4 + 2] = v.z; T[a][4 * c4 + 3] = v.w;
+                    }
+                for (int it = 0; it < iters; ++it) {
+                    const int k = q + 4 * it;
+                    if (k < n && k != i) {
+                        float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2) {
+                            const float4 hv = *reinterpret_cast<const float4*>(s.Hbuf + k * 36 + 4 * c2);   // (c,x),(c,y),(c+1,x),(c+1,y)
+                            t00 = fmaf(T[0][2 * c2], hv.x, fmaf(T[0][2 * c2 + 1], hv.z, t00));
+                            t01 = fmaf(T[0][2 * c2], hv.y, fmaf(T[0][2 * c2 + 1], hv.w, t01));
+                            t10 = fmaf(T[1][2 * c2], hv.x, fmaf(T[1][2 * c2 + 1], hv.z, t10));
+                            t11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, t11));
+                        }
+                        if (rv) {
+                            float4 v = s.J[row * pB + k];
+                            v.x += t00; v.y += t01; v.z += t10; v.w += t11;
+                            s.J[row * pB + k] = v;
+                        }
+                        rs[0] += t00; rs[1] += t01; rs[2] += t10; rs[3] += t11;
+                    }
                 }
 #pragma unroll
                 for (int t = 0; t < 4; ++t) rs[t] = quad_sum(rs[t]);
-                // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
-                const float4 dg = make_float4(1.f - rs[0], -rs[1], -rs[2], 1.f - rs[3]);
-#pragma unroll
-                for (int it = 0; it < NIT; ++it)
-                    if (4 * it + q == row) Jr[it] = dg;
+                if (rv && q == 0) {          // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
+                    s.J[row * pB + row] = make_float4(1.f - rs[0], -rs[1], -rs[2], 1.f - rs[3]);
+                }
             }
-            if ((p.out_jac && step == 0) || use_pivot) {     // rare paths need the assembled J in shared memory
-                __syncthreads();
-                if (rv) {
-#pragma unroll
-                    for (int it = 0; it < NIT; ++it)
-                        if (4 * it + q < n) s.J[row * pB + 4 * it + q] = Jr[it];
+            __syncthreads();
+            if (p.out_jac && step == 0) {
+                float* oj = p.out_jac + (size_t)b * N2 * N2;
+                for (int t = tid; t < N2 * N2; t += NW * 32) {
+                    const int rr = t / N2, cc = t - rr * N2;
+                    oj[t] = reinterpret_cast<const float*>(s.J)[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)];
                 }
                 __syncthreads();
-                if (p.out_jac && step == 0) {
-                    float* oj = p.out_jac + (size_t)b * N2 * N2;
-                    for (int t = tid; t < N2 * N2; t += NW * 32) {
-                        const int rr = t / N2, cc = t - rr * N2;
-                        oj[t] = reinterpret_cast<const float*>(s.J)[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)];
-                    }
-                }
             }
 
-            // ---------------- Jacobian LU:  log|det J| --------------------------------------------------------
-            // J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU on the register-
-            // resident blocks.  Step k: every row below k eliminates block column k with the published pivot line
-            // k (and -P_kk^{-1}); row k+1 -- whose blocks are final after this update -- inverts its diagonal block
-            // and publishes line k+1 in the same step (look-ahead: the reciprocal chain overlaps the remaining
-            // updates), so there is ONE barrier per step.  Rows are contiguous per warp: a warp whose rows are all
-            // finished only keeps the barrier count.  log|det J| = sum_k log|det P_kk|.
-            // Multipliers and pivot determinants are monitored; if they leave the safe range the whole evaluation
-            // is redone with the partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
-            float lacc = 0.f;                         // log2|det P_kk| of the pivots this thread owned
-            if (!use_pivot) {
+            // ---------------- LU phase: real 2n x 2n FP32 Jacobian || complex n x n FP64 Slater matrix ---------
+            // Jacobian: J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU, one
+            // thread per block-row (2 rows), blocks in shared memory: log|det J| = sum_k log|det P_kk|.  Half the
+            // sequential depth of a scalar LU, no pivot search, no cross-warp exchange.  Multipliers and pivot
+            // determinants are monitored; if they leave the safe range the whole evaluation is redone with the
+            // partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
+            if (!use_pivot && warp < nBw) {
+                const int bi = tid;
+                const bool act = bi < n;
+                float4* brow = s.J + (act ? bi : 0) * pB;
+                float lacc = 0.f;
                 bool bad = false;
-                auto publish_inv = [&](const float4 pk, float4* line) {     // by the one thread that owns P_kk
+                for (int k = 0; k < n; ++k) {
+                    if (nBw > 1) named_bar_sync(1, nBw * 32); else __syncwarp();
+                    const float4* prow = s.J + k * pB;
+                    const float4 pk = prow[k];                              // pivot block (broadcast)
                     const float det = pk.x * pk.w - pk.y * pk.z;
                     const float idet = rcp_approx(det);
-                    lacc += lg2_approx(fabsf(det));
+                    lacc += lg2_approx(fabsf(det));                          // identical in every lane
                     bad |= !(fabsf(det) > 0.05f);                            // also catches NaN
-                    line[n8] = make_float4(-pk.w * idet, pk.y * idet, pk.z * idet, -pk.x * idet);   // -P^{-1}
-                };
-                if (row == 0) {
-                    if (q == 0) publish_inv(Jr[0], s.pvJ);
-#pragma unroll
-                    for (int it = 0; it < NIT; ++it) s.pvJ[4 * it + q] = Jr[it];
-                }
-                __syncthreads();
-#pragma unroll
-                for (int kb = 0; kb < NIT; ++kb) {
-#pragma unroll 1
-                    for (int kq = 0; kq < 4; ++kq) {
-                        const int k = 4 * kb + kq;
-                        if (k >= n) break;
-                        if (8 * warp + 7 > k) {                             // warp-uniform: some row of this warp is below the pivot
-                            const float4* line = s.pvJ + (k & 1) * (n8 + 1);
-                            float4* nline = s.pvJ + ((k + 1) & 1) * (n8 + 1);
-                            const float4 a = shfl4(Jr[kb], qbase + kq);     // column-k block of the own row
-                            if (rv && row > k) {
-                                const float4 m = line[n8];
-                                const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
-                                const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
-                                bad |= fmaxf(fmaxf(fabsf(l00), fabsf(l01)), fmaxf(fabsf(l10), fabsf(l11))) > 2.f;
-                                const bool nxt = row == k + 1;
-#pragma unroll
-                                for (int it = kb; it < NIT; ++it) {
-                                    if (it > kb || q > kq) {
-                                        const float4 pv = line[4 * it + q];
-                                        float4 v = Jr[it];
-                                        v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
-                                        v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
-                                        v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
-                                        v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
-                                        Jr[it] = v;
-                                    }
-                                    // the next pivot block P_{k+1,k+1} is final now: invert it early
-                                    if (it == kb && kq < 3 && nxt && q == kq + 1) publish_inv(Jr[it], nline);
-                                    if (it == kb + 1 && kq == 3 && nxt && q == 0) publish_inv(Jr[it], nline);
-                                }
-                                if (nxt) {
-#pragma unroll
-                                    for (int it = kb; it < NIT; ++it) nline[4 * it + q] = Jr[it];
-                                }
-                            }
+                    if (act && bi > k) {
+                        const float4 a = brow[k];
+                        // -L = -A_ik P_kk^{-1},  P^{-1} = [[w,-y],[-z,x]] / det
+                        const float l00 = (a.y * pk.z - a.x * pk.w) * idet, l01 = (a.x * pk.y - a.y * pk.x) * idet;
+                        const float l10 = (a.w * pk.z - a.z * pk.w) * idet, l11 = (a.z * pk.y - a.w * pk.x) * idet;
+                        bad |= (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
+#pragma unroll 4
+                        for (int j = k + 1; j < n; ++j) {
+                            const float4 qv = prow[j];
+                            float4 v = brow[j];
+                            v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
+                            v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
+                            v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
+                            v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
+                            brow[j] = v;
                         }
-                        __syncthreads();
                     }
                 }
-                if (bad) s.flag[2] = 1;
-                __syncthreads();
-                if (s.flag[2]) {                     // block-uniform: redo this evaluation with the pivoted LU
-                    use_pivot = true;
-                    if (tid == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
-                    continue;
-                }
-            } else {
-                // ---- fallback: scalar LU with partial pivoting on the blocked shared-memory copy, one thread per row.
+                if (__any_sync(0xffffffffu, bad) && lane == 0) s.flag[2] = 1;
+                if (tid == 0) s.lsum[0] = (double)lacc * 0.693147180559945309417;
+            } else if (use_pivot && warp < nJw) {
+                // ---- fallback: scalar LU with partial pivoting on the blocked storage, one thread per row.
                 // |a| bits with the row id in the low 7 bits -> one REDUX per warp; per-warp maxima exchanged
                 // through a double-buffered slot, one named barrier per elimination step.
-                if (warp < nJw) {
-                    const int r = tid;
-                    float* Jf = reinterpret_cast<float*>(s.J);
-                    auto el = [&](int rr, int cc) -> float& { return Jf[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)]; };
-                    bool done = !(r < N2);
-                    float mylog = 0.f;
-                    for (int k = 0; k < N2; ++k) {
-                        const float cur = done ? 0.f : el(r, k);
-                        const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
-                        const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                        if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
-                        if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
-                        unsigned gmax = s.redJ[(k & 1) * 8];
+                const int r = tid;
+                float* Jf = reinterpret_cast<float*>(s.J);
+                auto el = [&](int rr, int cc) -> float& { return Jf[((rr >> 1) * pB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)]; };
+                bool done = !(r < N2);
+                float mylog = 0.f;
+                for (int k = 0; k < N2; ++k) {
+                    const float cur = done ? 0.f : el(r, k);
+                    const unsigned key = done ? 0u : ((__float_as_uint(fabsf(cur)) & ~0x7Fu) | (unsigned)r);
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0) s.redJ[(k & 1) * 8 + warp] = wmax;
+                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
+                    unsigned gmax = s.redJ[(k & 1) * 8];
 #pragma unroll
-                        for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
-                        const int pr = (int)(gmax & 0x7Fu);
-                        const float piv = el(pr, k);
-                        if (r == pr) {
-                            done = true;
-                            mylog = lg2_approx(fabsf(piv));
-                        } else if (!done) {
-                            const float l = -cur / piv;
-                            for (int j = k + 1; j < N2; ++j) el(r, j) = fmaf(l, el(pr, j), el(r, j));
-                        }
-                        if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
+                    for (int w = 1; w < nJw; ++w) gmax = max(gmax, s.redJ[(k & 1) * 8 + w]);
+                    const int pr = (int)(gmax & 0x7Fu);
+                    const float piv = el(pr, k);
+                    if (r == pr) {
+                        done = true;
+                        mylog = lg2_approx(fabsf(piv));
+                    } else if (!done) {
+                        const float l = -cur / piv;
+                        for (int j = k + 1; j < N2; ++j) el(r, j) = fmaf(l, el(pr, j), el(r, j));
                     }
-                    lacc = mylog;
+                    if (nJw > 1) named_bar_sync(1, nJw * 32); else __syncwarp();
                 }
-                __syncthreads();
+                double acc = (double)mylog;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s.lsum[8 + warp] = acc * 0.693147180559945309417;
             }
-
-            // ---------------- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + dz/L ----------------
-            // (src/slater.py:14-17; the twist and any common displacement are pure row/column phases and drop out of
-            // |det|).  Thread (row, q) builds and keeps the entries of columns j = 4it+q in registers.
-            double2 Dr[NIT];
-            {
+            if (warp >= NW - nSw) {
+                // ---- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + (dz - mean dz)/L
+                // (src/slater.py:14-17; the twist and the common displacement are pure row/column phases
+                // and drop out of |det|).  All warps >= nJw build entries; the first nDw of them factorise.
+                constexpr int nb = nSw * 32;
+                const int t2 = tid - nJw * 32;
                 const int mmax = s.flag[1];                      // max |m| over this walker's occupied orbitals
-                const bool tables = mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes;
-                if (tables) {
+                if (mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes) {
                     // power tables  X_r^m = e^{2 pi i m w_rx},  Y_r^m,  m = 1..mmax  (one sincospi per coordinate)
-                    if (tid < N2) {
-                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[tid], invL,
-                                              reinterpret_cast<const double*>(s.us)[tid]);
+                    for (int c = t2; c < 2 * n; c += nb) {
+                        const int rr = c >> 1, comp = c & 1;
+                        double mean = 0.0;
+                        for (int t = 0; t < n; ++t) mean += reinterpret_cast<const double*>(s.dz)[2 * t + comp];
+                        mean /= (double)n;
+                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[c] - mean, invL,
+                                              reinterpret_cast<const double*>(s.us)[c]);
                         double sn, cs;
                         sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
-                        double2* tb = s.ptab + (size_t)tid * mmax;   // [row][comp][m-1]
+                        double2* tb = s.ptab + (size_t)c * mmax;   // [row][comp][m-1]
                         double2 pw = make_double2(cs, sn);
                         tb[0] = pw;
                         for (int m = 1; m < mmax; ++m) {
@@ -752,155 +647,121 @@ sweep_kernel(const SweepParams p) {
                             tb[m] = pw;
                         }
                     }
-                    __syncthreads();
+                    if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
+                    for (int j = t2 >> 5; j < n; j += nb / 32) {
+                        const int rr = t2 & 31;
+                        const int2 mk = s.kint[j];
 #pragma unroll
-                    for (int it = 0; it < NIT; ++it) {
-                        const int j = 4 * it + q;
-                        double2 v = make_double2(0.0, 0.0);
-                        if (rv && j < n) {
-                            const int2 mk = s.kint[j];
-                            const int ax = abs(mk.x), ay = abs(mk.y);
-                            double2 X = make_double2(1.0, 0.0), Y = make_double2(1.0, 0.0);
-                            if (ax) { X = s.ptab[(size_t)(2 * row) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
-                            if (ay) { Y = s.ptab[(size_t)(2 * row + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
-                            v = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                        for (int half = 0; half < (NW > 4 ? 2 : 1); ++half) {
+                            const int r2 = rr + 32 * half;
+                            if (r2 < n) {
+                                const int ax = abs(mk.x), ay = abs(mk.y);
+                                double2 X = make_double2(1.0, 0.0), Y = make_double2(1.0, 0.0);
+                                if (ax) { X = s.ptab[(size_t)(2 * r2) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
+                                if (ay) { Y = s.ptab[(size_t)(2 * r2 + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
+                                s.D[r2 * pD + j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                            }
                         }
-                        Dr[it] = v;
                     }
                 } else {
-                    const double2 uu = s.us[i], dd = s.dz[i];
-                    const double wx = fma(dd.x, invL, uu.x), wy = fma(dd.y, invL, uu.y);
-#pragma unroll
-                    for (int it = 0; it < NIT; ++it) {
-                        const int j = 4 * it + q;
-                        double2 v = make_double2(0.0, 0.0);
-                        if (rv && j < n) {
-                            const int2 mk = s.kint[j];
-                            double ph = fma((double)mk.x, wx, (double)mk.y * wy);
-                            ph -= rint(ph);
-                            double sn, cs;
-                            sincospi(2.0 * ph, &sn, &cs);
-                            v = make_double2(cs, sn);
-                        }
-                        Dr[it] = v;
+                    double mx = 0.0, my = 0.0;
+                    for (int t = 0; t < n; ++t) { const double2 v = s.dz[t]; mx += v.x; my += v.y; }
+                    mx /= (double)n; my /= (double)n;
+                    for (int idx = t2; idx < n * n; idx += nb) {
+                        const int rr = idx / n, j = idx - rr * n;
+                        const double2 uu = s.us[rr], dd = s.dz[rr];
+                        const double wx = fma(dd.x - mx, invL, uu.x), wy = fma(dd.y - my, invL, uu.y);
+                        const int2 mk = s.kint[j];
+                        double ph = fma((double)mk.x, wx, (double)mk.y * wy);
+                        ph -= rint(ph);
+                        double sn, cs;
+                        sincospi(2.0 * ph, &sn, &cs);
+                        s.D[rr * pD + j] = make_double2(cs, sn);
                     }
                 }
-            }
-            // ---------------- Slater LU: partially pivoted (implicit row exchange), register-resident rows ----------
-            // ONE barrier per step.  After eliminating column k every unfinished row offers its column-(k+1) entry;
-            // a REDUX picks the warp's best candidate, whose quad speculatively publishes its (already final) row
-            // into the warp's line together with 1/candidate -- the reciprocal chain overlaps the remaining updates.
-            // After the barrier all threads take the best of the NW warp candidates: pivot row, its line, its inverse.
-            // log|det D| = sum over pivots of log|pivot|.
-            bool singular = false;                    // a zero pivot column: det D = 0 (block-uniform)
-            double mypn = 1.0;                        // |pivot|^2 of the pivot this thread owned (log taken once, at the end)
-            {
-                bool done = !rv;
-                double2* lines = s.pvD;                                            // [2][NW][n8]
-                double2* sinv = reinterpret_cast<double2*>(smem_raw + L_::o_pv + 4 * n8 * n8);   // [2][8] 1/candidate
-                double* spn = reinterpret_cast<double*>(sinv + 16);                // [2][8] |candidate|^2
-                unsigned* skey = reinterpret_cast<unsigned*>(spn + 16);            // [2][8] candidate keys
-                // offer the column-`col` entry e (held by lane qe of each row) as this warp's pivot candidate
-                auto offer = [&](const double2 e, const int qe, const int par, bool& win) -> unsigned {
-                    const float mag = (float)(fabs(e.x) + fabs(e.y));
-                    const unsigned key = (!done && q == qe) ? ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)row) : 0u;
-                    const unsigned wk = __reduce_max_sync(0xffffffffu, key);
-                    win = !done && row == (int)(wk & 0x7Fu) && (wk >> 7) != 0u;
-                    if (win && q == qe) {
-                        const double pn = fma(e.x, e.x, e.y * e.y);
-                        double ip = (double)rcp_approx((float)pn);                 // 1/pn: FP32 seed + 2 Newton steps
-                        ip = ip * (2.0 - pn * ip);
-                        ip = ip * (2.0 - pn * ip);
-                        sinv[par * 8 + warp] = make_double2(e.x * ip, -e.y * ip);
-                        spn[par * 8 + warp] = pn;
+                if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
+                if (warp < nJw + nDw) {
+                    const int dw = warp - nJw;
+                    const int r = t2;
+                    double2* base = s.D + (r < n ? r : 0) * pD;
+                    bool done = !(r < n);
+                    double mylog = 0.0;
+                    double2 cur = done ? make_double2(0.0, 0.0) : base[0];
+                    unsigned wnext;
+                    {
+                        const float mag = (float)(fabs(cur.x) + fabs(cur.y));
+                        const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
+                        wnext = __reduce_max_sync(0xffffffffu, key);
+                        if (nDw > 1 && lane == 0) s.redD[dw] = wnext;
                     }
-                    return wk;
-                };
-                {
-                    bool win;
-                    const unsigned wk = offer(Dr[0], 0, 0, win);
-                    if (win) {
+                    for (int k = 0; k < n; ++k) {
+                        unsigned gmax = wnext;
+                        if (nDw > 1) {
+                            named_bar_sync(2, nDw * 32);
 #pragma unroll
-                        for (int it = 0; it < NIT; ++it) lines[warp * n8 + 4 * it + q] = Dr[it];
-                    }
-                    if (lane == 0) skey[warp] = wk;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int kb = 0; kb < NIT; ++kb) {
-#pragma unroll 1
-                    for (int kq = 0; kq < 4; ++kq) {
-                        const int k = 4 * kb + kq;
-                        if (k >= n) break;
-                        const int par = k & 1;
-                        unsigned gmax = skey[par * 8];
-                        int wbest = 0;
-#pragma unroll
-                        for (int w = 1; w < NW; ++w) {
-                            const unsigned kw = skey[par * 8 + w];
-                            if (kw > gmax) { gmax = kw; wbest = w; }
+                            for (int w = 0; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                        } else {
+                            __syncwarp();
                         }
                         const int pr = (int)(gmax & 0x7Fu);
-                        singular |= (gmax >> 7) == 0u;
-                        const double2 c = shfl2d(Dr[kb], qbase + kq);      // column-k entry of the own row (the pivot on row pr)
-                        if (row == pr && !done) {
-                            if (q == kq) mypn = spn[par * 8 + wbest];
+                        const double2* prow = s.D + pr * pD;
+                        const double2 piv = prow[k];
+                        const double pn = fma(piv.x, piv.x, piv.y * piv.y);
+                        if (r == pr) {
                             done = true;
+                            mylog = pn;                            // log taken once, after the loop
                         }
-                        const double2* line = lines + (par * NW + wbest) * n8;
+                        const bool upd = !done;
                         double lx = 0.0, ly = 0.0;
-                        if (!done) {
-                            const double2 iv = sinv[par * 8 + wbest];
-                            lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
-                            ly = -(c.x * iv.y + c.y * iv.x);
-                        }
-                        bool win = false;
-                        unsigned wk = 0u;
-#pragma unroll
-                        for (int it = kb; it < NIT; ++it) {
-                            if (!done && (it > kb || q > kq)) {
-                                const double2 pv = line[4 * it + q];
-                                double2 v = Dr[it];
+                        if (upd) {
+                            double ip = (double)rcp_approx((float)pn);   // 1/pn: FP32 seed + 2 Newton steps
+                            ip = ip * (2.0 - pn * ip);
+                            ip = ip * (2.0 - pn * ip);               // l = -cur / piv
+                            lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
+                            ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
+                            if (k + 1 < n) {
+                                const double2 pv = prow[k + 1];
+                                double2 v = base[k + 1];
                                 v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
                                 v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                                Dr[it] = v;
+                                base[k + 1] = v;
+                                cur = v;
                             }
-                            // column k+1 is final now: offer it as the next pivot candidate (look-ahead)
-                            if (it == kb && kq < 3 && k + 1 < n) wk = offer(Dr[it], kq + 1, par ^ 1, win);
-                            if (it == kb + 1 && kq == 3 && k + 1 < n) wk = offer(Dr[it], 0, par ^ 1, win);
                         }
-                        if (k + 1 < n) {
-                            if (win) {
-                                double2* nl = lines + ((par ^ 1) * NW + warp) * n8;
-#pragma unroll
-                                for (int it = kb; it < NIT; ++it) nl[4 * it + q] = Dr[it];
+                        {
+                            const float mag = (float)(fabs(cur.x) + fabs(cur.y));
+                            const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
+                            wnext = __reduce_max_sync(0xffffffffu, key);
+                            if (nDw > 1 && lane == 0) s.redD[((k + 1) & 1) * 8 + dw] = wnext;
+                        }
+                        if (upd) {
+#pragma unroll 2
+                            for (int j = k + 2; j < n; ++j) {
+                                const double2 pv = prow[j];
+                                double2 v = base[j];
+                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                base[j] = v;
                             }
-                            if (lane == 0) skey[(par ^ 1) * 8 + warp] = wk;
                         }
-                        __syncthreads();
                     }
-                }
-            }
-            // ---------------- block reduction of the two log-determinants -----------------------------------------
-            {
-                double aJ = (double)lacc * 0.693147180559945309417;
-                double aD = (mypn != 1.0) ? 0.5 * log(mypn) : 0.0;
+                    double acc = (r < n) ? 0.5 * log(mylog) : 0.0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    aJ += __shfl_xor_sync(0xffffffffu, aJ, o);
-                    aD += __shfl_xor_sync(0xffffffffu, aD, o);
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) s.lsum[warp] = acc;
                 }
-                if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
-                if (lane == 0) { s.lsum[warp] = aD; s.lsum[8 + warp] = aJ; }
             }
             __syncthreads();
-            break;
+            if (use_pivot || s.flag[2] == 0) break;
+            use_pivot = true;
+            if (tid == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
           }
 
             // ---------------- Metropolis accept / reject (MCMC.py:28-33) ------------------------------
             if (tid == 0) {
                 double ldJ = 0.0, ldD = 0.0;
-                for (int w = 0; w < NW; ++w) { ldD += s.lsum[w]; ldJ += s.lsum[8 + w]; }
+                if (use_pivot) { for (int w = 0; w < nJw; ++w) ldJ += s.lsum[8 + w]; } else { ldJ = s.lsum[0]; }
+                for (int w = nJw; w < nJw + nDw; ++w) ldD += s.lsum[w];
                 ldD -= (double)n * log(p.L);                     // D carries L^{-dim/2} per entry (slater.py:17)
                 const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179
                 int acc = 1;

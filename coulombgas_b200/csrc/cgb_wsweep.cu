@@ -1,0 +1,913 @@
+// Warp-per-walker Metropolis sweep / batched log p kernel for sm_100a (n <= 32).
+//
+// One WARP evaluates  log p = 2 log|det D| + log|det J|  (src/logpsi.py:22-31,179) of one walker: lane i owns
+// particle i, i.e. row i of the pair tensor (src/flow.py:22-26,46), block-row i of the flow Jacobian (which
+// replaces jax.jacfwd, src/logpsi.py:27-28) and row i of the Slater matrix (src/slater.py:14-17).  Consequences:
+//   * no block barrier anywhere: every exchange is a broadcast LDS from the warp's private shared-memory slice
+//     or a warp collective (REDUX / SHFL), ordered by __syncwarp; 12 independent warps per SM hide each
+//     other's latency chains (the two LU factorisations are sequential in the pivot index);
+//   * the weights are operands from the CONSTANT bank (FFMA/DFMA R, R, c[3][..], R): no register, no LDS;
+//   * both LU factorisations are register-resident AND rolled loops: every elimination step shifts the row one
+//     register to the left while it updates it (the FMA writes position j-1), so the active column is always
+//     register 0 and the loop body has compile-time register indices; the shrinking tail is cut by warp-uniform
+//     breaks.  Only the pivot line travels through a double-buffered shared-memory line.  The whole kernel is
+//     ~5k SASS instructions, so 12 warps in different phases still run out of the instruction cache (a fully
+//     unrolled first version, 330 kB of code, spent 47 % of its stall samples on instruction fetch).
+//     J: unpivoted 2x2-block LU (J = I + small for any physical flow; monitored, with a partially pivoted
+//     shared-memory LU as fallback).  D: partially pivoted complex float64 LU with implicit row exchange, pivot
+//     search by one REDUX per step;
+//   * the Metropolis chain (src/MCMC.py:22-34) is scheduled at the granularity of ONE proposal through a bounded
+//     multi-producer/multi-consumer ready queue in global memory: a free warp pops the walker that has been ready
+//     longest, evaluates one proposal, writes the walker state (x, log p, accept count; L2-resident) and pushes
+//     the walker back.  Every resident warp is busy until the last proposal, whatever the batch size (no wave
+//     quantisation, no head-of-line blocking).
+// Precision: FP32 pair passes with Kahan-compensated partner sums, float64 single-particle stream, float64
+// Slater matrix and LU, float64 log-det sums and Metropolis test.
+#include "cgb_common.cuh"
+#include <stdlib.h>
+#include "cgb_internal.h"
+
+namespace cgb {
+
+// ---------------------------------------------------------------------------------------------------
+// Constant-bank weight block.  FP32 copies feed the pair passes and the Jacobian-side contractions,
+// float64 copies feed the forward single-particle stream.  [in][out] like haiku's `w`.
+struct WConst {
+    float wt[5][16];      // Wt * log2(e)      two-particle layer (src/flow.py:46)
+    float bt[16];         // bt * log2(e)
+    float w0c[5][16];     // W0[4:9]           rows that see mean_j t0_ij (flow.py:34-36; s0 == 0, flow.py:16-18)
+    float w1a[16][16];    // W1[0:16]          acts on h_i
+    float w1b[16][16];    // W1[16:32]         acts on mean_k h_k
+    float w1c[16][16];    // W1[32:48]         acts on mean_j t_ij
+    float wf[16][2];      // Wf
+    double dw0c[5][16];
+    double db0[16];
+    double dw1a[16][16];
+    double dw1c[16][16];
+    double db1[16];
+    double dwf[16][2];
+};
+static_assert(sizeof(WConst) <= 11264, "WS_WCONST staging area too small");
+__constant__ WConst cW;
+
+__global__ void prep_wconst_kernel(const double* __restrict__ p, WConst* __restrict__ w) {
+    // source offsets in the flat 1074 vector (include/cgb200.h)
+    constexpr int S_WT = 0, S_BT = 80, S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
+    constexpr double LOG2E = 1.4426950408889634;
+    for (int t = threadIdx.x; t < 80; t += blockDim.x) {
+        (&w->wt[0][0])[t] = (float)(p[S_WT + t] * LOG2E);
+        (&w->w0c[0][0])[t] = (float)p[S_W0 + 64 + t];
+        (&w->dw0c[0][0])[t] = p[S_W0 + 64 + t];
+    }
+    for (int t = threadIdx.x; t < 16; t += blockDim.x) {
+        w->bt[t] = (float)(p[S_BT + t] * LOG2E);
+        w->db0[t] = p[S_B0 + t];
+        w->db1[t] = p[S_B1 + t];
+    }
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        (&w->w1a[0][0])[t] = (float)p[S_W1 + t];
+        (&w->w1b[0][0])[t] = (float)p[S_W1 + 256 + t];
+        (&w->w1c[0][0])[t] = (float)p[S_W1 + 512 + t];
+        (&w->dw1a[0][0])[t] = p[S_W1 + t];
+        (&w->dw1c[0][0])[t] = p[S_W1 + 512 + t];
+    }
+    for (int t = threadIdx.x; t < 32; t += blockDim.x) {
+        (&w->wf[0][0])[t] = (float)p[S_WF + t];
+        (&w->dwf[0][0])[t] = p[S_WF + t];       // bf dropped: a common shift of z is a global phase of det D
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-warp shared-memory slice
+template <int N>
+struct WLay {
+    static constexpr int PB = N | 1;                      // float4 blocks per staged Jacobian block-row (odd: conflict-free)
+    static constexpr int J_bytes = 16 * N * PB;
+    // early aliases inside the J region (all dead before pass 2 writes J):
+    static constexpr int a_sig0 = 0;                      // float[N][20]   sigma0 (pitch 20: conflict-free LDS/STS.128)
+    static constexpr int a_hbuf = 80 * N;                 // double[N][17]  h_i (float64)
+    static constexpr int a_scr = 80 * N;                  // float[N][68]   R|T rows (overlays h once the forward pass is done)
+    static constexpr int a_s1 = a_scr + 272 * N;          // float[N][20]   sigma1
+    static constexpr int a_hbar = a_s1 + 80 * N;          // double[16]
+    static constexpr int a_gb = a_hbar + 128;             // double[16]
+    static constexpr int alias_bytes = a_gb + 128;
+    static constexpr int RJ = ((J_bytes > alias_bytes ? J_bytes : alias_bytes) + 15) & ~15;
+    static constexpr int o_J = 0;
+    static constexpr int o_H = RJ;                        // float[N][16][2] H_k; afterwards the LU pivot lines
+    static constexpr int H_bytes = 128 * N > 32 * (N + 4) ? 128 * N : 32 * (N + 4);
+    static constexpr int o_pos = o_H + H_bytes;           // float4[N] half-angle table
+    static constexpr int o_k = o_pos + 16 * N;            // int2[N]   integer part of the occupied k rows
+    static constexpr int total = (o_k + 8 * N + 15) & ~15;
+    // late aliases of the J region: Slater power tables double2[N][PT], PT = (2*(mmax+1))|1, or (large |m|) the
+    // staged Slater rows double2[N][PB]
+    static constexpr int MMAX_TAB = (RJ / (16 * N) - 1) / 2 - 1;
+    static_assert(16 * N * PB <= RJ, "Slater staging must fit the J region");
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#ifndef CGBW_KAHAN
+#define CGBW_KAHAN 1        // 0: plain FP32 partner sums (precision experiment)
+#endif
+__device__ __forceinline__ void kahan_add_w(float& sum, float& comp, float x) {
+#if !CGBW_KAHAN
+    sum += x;
+    return;
+#endif
+    const float y = x - comp;
+    const float t = sum + y;
+    comp = (t - sum) - y;
+    sum = t;
+}
+// float64 softplus (forward value) + FP32 logistic sigmoid (Jacobian side) of a float64 pre-activation.
+// softplus(x) = max(x,0) + log1p(t), t = exp(-|x|): exp by range reduction + degree-10 Taylor,
+// log1p(t) = 2 atanh(t/(2+t)) by a degree-10 series in u^2 <= 1/9 with a Newton-refined FP32 reciprocal (~1e-14).
+__device__ __forceinline__ void softplus_sigmoid_f64w(double pre, double& sp, float& sg) {
+    const double y = fmax(-fabs(pre) * 1.4426950408889634074, -1000.0);
+    const double kf = rint(y);
+    const double f = (y - kf) * 0.69314718055994530942;
+    double pz = 2.7557319223985891e-07;
+    pz = fma(pz, f, 2.7557319223985893e-06);
+    pz = fma(pz, f, 2.4801587301587302e-05);
+    pz = fma(pz, f, 1.9841269841269841e-04);
+    pz = fma(pz, f, 1.3888888888888889e-03);
+    pz = fma(pz, f, 8.3333333333333332e-03);
+    pz = fma(pz, f, 4.1666666666666664e-02);
+    pz = fma(pz, f, 1.6666666666666666e-01);
+    pz = fma(pz, f, 0.5);
+    pz = fma(pz, f, 1.0);
+    pz = fma(pz, f, 1.0);
+    const double t = pz * __hiloint2double(((int)kf + 1023) << 20, 0);
+    const double d = 2.0 + t;
+    const double r0 = (double)rcp_approx((float)d);
+    const double r = fma(r0, fma(-d, r0, 1.0), r0);
+    const double u = t * r, w = u * u;
+    double a = 4.7619047619047616e-02;
+    a = fma(a, w, 5.2631578947368418e-02);
+    a = fma(a, w, 5.8823529411764705e-02);
+    a = fma(a, w, 6.6666666666666666e-02);
+    a = fma(a, w, 7.6923076923076927e-02);
+    a = fma(a, w, 9.0909090909090912e-02);
+    a = fma(a, w, 1.1111111111111111e-01);
+    a = fma(a, w, 1.4285714285714285e-01);
+    a = fma(a, w, 0.2);
+    a = fma(a, w, 3.3333333333333331e-01);
+    a = fma(a, w, 1.0);
+    sp = fmax(pre, 0.0) + 2.0 * u * a;
+    const float ef = (float)t, rr = rcp_approx(1.f + ef);
+    sg = pre >= 0.0 ? rr : ef * rr;
+}
+
+// pair features of (row i, partner j) from the half-angle table (cos, sin of pi*u): cos/sin of
+// theta = 2 pi (x_i - x_j)/L by angle addition and d^2 = sin^2(theta_x/2) + sin^2(theta_y/2)  (src/flow.py:22-25)
+struct WPairFeat { float cx, cy, sx, sy, d2; };
+__device__ __forceinline__ WPairFeat wpair_features(const float4 pi_, const float4 pj) {
+    const float shx = pi_.y * pj.x - pi_.x * pj.y, chx = fmaf(pi_.x, pj.x, pi_.y * pj.y);
+    const float shy = pi_.w * pj.z - pi_.z * pj.w, chy = fmaf(pi_.z, pj.z, pi_.w * pj.w);
+    WPairFeat f;
+    f.cx = fmaf(-2.f * shx, shx, 1.f);
+    f.cy = fmaf(-2.f * shy, shy, 1.f);
+    f.sx = 2.f * shx * chx;
+    f.sy = 2.f * shy * chy;
+    f.d2 = fmaf(shx, shx, shy * shy);
+    return f;
+}
+
+// Partially pivoted scalar LU of the staged Jacobian (blocked shared-memory layout), one warp, lane owns scalar
+// rows lane and lane+32.  Fallback of the unpivoted register LU; returns this lane's sum of log2|pivot|.
+template <int N>
+__device__ __noinline__ float pivoted_lu_smem(float* Jf, int lane) {
+    constexpr int PB = WLay<N>::PB, N2 = 2 * N;
+    auto el = [&](int rr, int cc) -> float& { return Jf[((rr >> 1) * PB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)]; };
+    const int r0 = lane, r1 = lane + 32;
+    bool d0 = !(r0 < N2), d1 = !(r1 < N2);
+    float mylog = 0.f;
+    for (int k = 0; k < N2; ++k) {
+        const float c0 = d0 ? 0.f : el(r0, k), c1 = d1 ? 0.f : el(r1, k);
+        const unsigned k0 = d0 ? 0u : ((__float_as_uint(fabsf(c0)) & ~0x3Fu) | (unsigned)r0);
+        const unsigned k1 = d1 ? 0u : ((__float_as_uint(fabsf(c1)) & ~0x3Fu) | (unsigned)r1);
+        const unsigned g = __reduce_max_sync(0xffffffffu, max(k0, k1));
+        const int pr = (int)(g & 0x3Fu);
+        const float piv = el(pr, k);
+        if (!d0) {
+            if (r0 == pr) { d0 = true; mylog += lg2_approx(fabsf(piv)); }
+            else { const float l = -c0 / piv; for (int j = k + 1; j < N2; ++j) el(r0, j) = fmaf(l, el(pr, j), el(r0, j)); }
+        }
+        if (!d1) {
+            if (r1 == pr) { d1 = true; mylog += lg2_approx(fabsf(piv)); }
+            else { const float l = -c1 / piv; for (int j = k + 1; j < N2; ++j) el(r1, j) = fmaf(l, el(pr, j), el(r1, j)); }
+        }
+        __syncwarp();
+    }
+    return mylog;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ready queue (bounded MPMC, Vyukov style): slot = (sequence << 32) | walker.  Slot i starts "filled" with walker i
+// for i < B (every walker is ready for step 0) and "free for push i" otherwise; head = 0, tail = B.
+__global__ void wqueue_init_kernel(unsigned long long* slots, unsigned cap, unsigned B, unsigned long long* ctr) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) slots[i] = i < B ? (((unsigned long long)(i + 1) << 32) | i) : ((unsigned long long)i << 32);
+    if (i == 0) { ctr[0] = 0ull; ctr[1] = (unsigned long long)B; ctr[2] = 0ull; }    // head, tail, spin diagnostics
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using L_ = WLay<N>;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int PB = L_::PB;
+    const int lane = threadIdx.x & 31;
+    unsigned char* sm = smem_raw + (threadIdx.x >> 5) * L_::total;
+    float4* const sJ = reinterpret_cast<float4*>(sm + L_::o_J);
+    float* const sSig0 = reinterpret_cast<float*>(sm + L_::a_sig0);
+    double* const sHbuf = reinterpret_cast<double*>(sm + L_::a_hbuf);
+    float* const sScr = reinterpret_cast<float*>(sm + L_::a_scr);
+    float* const sS1 = reinterpret_cast<float*>(sm + L_::a_s1);
+    double* const sHbar = reinterpret_cast<double*>(sm + L_::a_hbar);
+    double* const sGb = reinterpret_cast<double*>(sm + L_::a_gb);
+    float* const sH = reinterpret_cast<float*>(sm + L_::o_H);
+    float4* const sPos = reinterpret_cast<float4*>(sm + L_::o_pos);
+    int2* const sK = reinterpret_cast<int2*>(sm + L_::o_k);
+    double2* const sPt = reinterpret_cast<double2*>(sm + L_::o_J);
+
+    const bool rv = lane < N;
+    const int kself = rv ? lane : N - 1;
+    const float invn = 1.f / (float)N;
+    const double invL = 1.0 / p.L;
+    const double nlogL = (double)N * log(p.L);               // D carries L^{-dim/2} per entry (slater.py:17)
+    const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
+    const unsigned long long total = (unsigned long long)p.B * (unsigned long long)(p.mc_steps + 1);
+    const unsigned long long qmask = (unsigned long long)p.qcap - 1ull;
+
+    for (;;) {
+        // ---------------- pop the walker that has been ready longest ---------------------------------------
+        int b = 0;
+        {
+            unsigned long long idx = 0;
+            if (lane == 0) idx = atomicAdd(p.qctr, 1ull);
+            idx = __shfl_sync(FULL, idx, 0);
+            if (idx >= total) break;
+            if (lane == 0) {
+                unsigned long long* slot = p.queue + (idx & qmask);
+                const unsigned want = (unsigned)(idx + 1ull);
+                unsigned long long v;
+                unsigned spins = 0;
+                while ((unsigned)((v = ld_acquire_u64(slot)) >> 32) != want) { __nanosleep(40); ++spins; }
+                if (spins) atomicAdd(p.qctr + 2, (unsigned long long)spins);
+                st_release_u64(slot, (unsigned long long)(unsigned)(idx + (unsigned long long)p.qcap) << 32);   // free for push idx+cap
+                b = (int)(unsigned)(v & 0xffffffffull);
+            }
+            b = __shfl_sync(FULL, b, 0);
+        }
+        __syncwarp();
+        const int step = p.mc_steps > 0 ? __ldcg(p.done + b) : 0;
+
+        // ---------------- walker state, proposal (MCMC.py:26), reduced coordinates -------------------------
+        double2 xv = make_double2(0.0, 0.0);
+        if (rv) xv = __ldcg(reinterpret_cast<const double2*>((step == 0 ? p.x : p.x_out) + ((size_t)b * N + lane) * 2));
+        double logp_cur = 0.0;
+        if (step > 0) logp_cur = __ldcg(p.ws_logp + b);
+        int mmax;
+        {
+            int2 mk = make_int2(0, 0);
+            if (rv) {
+                int si = __ldg(p.state_idx + (size_t)b * N + lane);
+                si = min(max(si, 0), p.M - 1);
+                mk.x = (int)rint(__ldg(p.ktable + 2 * si) - p.tw0);
+                mk.y = (int)rint(__ldg(p.ktable + 2 * si + 1) - p.tw1);
+                sK[lane] = mk;
+            }
+            mmax = __reduce_max_sync(FULL, max(abs(mk.x), abs(mk.y)));
+        }
+        if (step > 0) {
+            double nzx, nzy;
+            if (p.noise) {
+                double2 nz = make_double2(0.0, 0.0);
+                if (rv) nz = __ldg(reinterpret_cast<const double2*>(p.noise + (((size_t)(step - 1) * p.B + b) * N + lane) * 2));
+                nzx = nz.x; nzy = nz.y;
+            } else {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, (uint32_t)lane, 0u),
+                                              make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
+                float sn, cs;
+                sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
+                nzx = (double)(rad * cs); nzy = (double)(rad * sn);
+            }
+            xv.x += p.sigma * nzx;
+            xv.y += p.sigma * nzy;
+        }
+        double ux = xv.x * invL, uy = xv.y * invL;
+        ux -= floor(ux); uy -= floor(uy);                       // features are L-periodic (flow.py:22-25)
+        float4 pos;                                             // (cos, sin)(pi ux), (cos, sin)(pi uy)
+        {
+            float cs2[2], sn2[2];
+#pragma unroll 1
+            for (int comp = 0; comp < 2; ++comp) {
+                const double u = comp ? uy : ux;
+                const float uh = (float)u, ul = (float)(u - (double)uh);
+                float sn, cs;
+                sincospif(uh, &sn, &cs);                         // half angle pi*u, first-order hi/lo correction
+                const float pl = kPi * ul;
+                const float c1 = fmaf(-pl, sn, cs), s1_ = fmaf(pl, cs, sn);
+                if (comp) { cs2[1] = c1; sn2[1] = s1_; } else { cs2[0] = c1; sn2[0] = s1_; }
+            }
+            pos = make_float4(cs2[0], sn2[0], cs2[1], sn2[1]);
+        }
+        if (rv) sPos[lane] = pos;
+        __syncwarp();
+
+        // ---------------- pass 1: two-particle stream, means over partners (flow.py:34-36,46) ----------------
+        double dzx = 0.0, dzy = 0.0;
+        {
+            double md[16], m0d[5];
+            {
+                float m[16], mc[16], m0[5], m0c[5];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { m[c] = 0.f; mc[c] = 0.f; }
+#pragma unroll
+                for (int f = 0; f < 5; ++f) { m0[f] = 0.f; m0c[f] = 0.f; }
+                float4 pn = sPos[0];
+#pragma unroll 1
+                for (int k = 0; k < N; ++k) {
+                    const WPairFeat f = wpair_features(pos, pn);
+                    pn = sPos[k + 1 < N ? k + 1 : k];             // next partner's table entry ahead of its use
+                    const float d = sqrt_approx(f.d2);            // 0 on the diagonal (flow.py:25)
+                    kahan_add_w(m0[0], m0c[0], f.cx); kahan_add_w(m0[1], m0c[1], f.cy);
+                    kahan_add_w(m0[2], m0c[2], f.sx); kahan_add_w(m0[3], m0c[3], f.sy);
+                    kahan_add_w(m0[4], m0c[4], d);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
+                                        fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], cW.bt[c])))));
+                        kahan_add_w(m[c], mc[c], softplus2(a));
+                    }
+                }
+                const double invnd = 1.0 / (double)N;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) m0d[f] = ((double)m0[f] - (double)m0c[f]) * invnd;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) md[c] = ((double)m[c] - (double)mc[c]) * (0.693147180559945309417 * invnd);
+            }
+            // ---------------- single-particle stream (flow.py:45,51-55): forward values in float64 -----------
+            // rolled over groups of 4 output channels (uniform constant-bank indices)
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+                double hq[4];
+                float sq[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int c = 4 * c4 + kk;
+                    double pre = cW.db0[c];
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) pre = fma(m0d[f], cW.dw0c[f][c], pre);
+                    softplus_sigmoid_f64w(pre, hq[kk], sq[kk]);
+                }
+                if (rv) {
+                    *reinterpret_cast<float4*>(sSig0 + lane * 20 + 4 * c4) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) sHbuf[lane * 17 + 4 * c4 + kk] = hq[kk];
+                }
+            }
+            __syncwarp();
+            {   // hbar_c = mean_k h_k[c]  (lane c), then gb_c = sum_e hbar_e W1b[e][c]
+                const int c = lane & 15;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+                for (int r = 0; r + 1 < N; r += 2) { a0 += sHbuf[r * 17 + c]; a1 += sHbuf[(r + 1) * 17 + c]; }
+                if (N & 1) a0 += sHbuf[(N - 1) * 17 + c];
+                if (lane < 16) sHbar[c] = (a0 + a1) / (double)N;
+                __syncwarp();
+                double gbv = 0.0;
+                const double* w1b = p.params + 256 + 256 + c;       // W1[16+e][c]
+#pragma unroll
+                for (int e = 0; e < 16; ++e) gbv = fma(sHbar[e], __ldg(w1b + 16 * e), gbv);
+                if (lane < 16) sGb[c] = gbv;
+                __syncwarp();
+            }
+            double h[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) h[e] = sHbuf[kself * 17 + e];
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float sq[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int c = 4 * c4 + kk;
+                    double g0 = cW.db1[c] + sGb[c], g1 = 0.0, g2 = 0.0, g3 = 0.0;    // 4 chains per channel: DFMA latency
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        g0 = fma(h[e], cW.dw1a[e][c], g0); g1 = fma(md[e], cW.dw1c[e][c], g1);
+                        g2 = fma(h[e + 1], cW.dw1a[e + 1][c], g2); g3 = fma(md[e + 1], cW.dw1c[e + 1][c], g3);
+                    }
+                    const double g = (g0 + g1) + (g2 + g3);
+                    double sp;
+                    softplus_sigmoid_f64w(g, sp, sq[kk]);
+                    const double sv = sHbuf[kself * 17 + c] + sp;  // s_i (flow.py:52)
+                    dzx = fma(sv, cW.dwf[c][0], dzx);
+                    dzy = fma(sv, cW.dwf[c][1], dzy);
+                }
+                if (rv) *reinterpret_cast<float4*>(sS1 + lane * 20 + 4 * c4) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+            }
+        }
+        __syncwarp();
+
+        // ---------------- pass 2b: H_i = d hbar / d x_i = (1/n) [ sum_k P_k E_ki - P_i sum_k E_ik ] ------------
+        // P_k E_ki = sigma0_k . W0c^T (eps . E_ik), eps = (-,-,+,+,-): accumulate S[c][fd] = sum_k sigma0_k[c] E_ik[fd]
+        // over the 6 non-zero entries fd of E (96 FMA per pair) and contract with W0c once at the end.
+        {
+            float S[16][6];
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) S[c][q] = 0.f;
+            float sE[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // sum_k E_ik : (0x,2x,4x,1y,3y,4y)
+            float4 pn = sPos[0];
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                const float4 pj = pn;
+                pn = sPos[k + 1 < N ? k + 1 : k];
+                if (k != kself) {
+                    const WPairFeat f = wpair_features(pos, pj);
+                    const float i4d = 0.25f * rsqrt_approx(f.d2);
+                    float E[6];
+                    E[0] = alpha * f.sx; E[1] = -alpha * f.cx; E[2] = -E[0] * i4d;
+                    E[3] = alpha * f.sy; E[4] = -alpha * f.cy; E[5] = -E[3] * i4d;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 sk4 = *reinterpret_cast<const float4*>(sSig0 + k * 20 + 4 * c4);
+                        const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                            for (int q = 0; q < 6; ++q) S[4 * c4 + kk][q] = fmaf(skv[kk], E[q], S[4 * c4 + kk][q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) sE[q] += E[q];
+                }
+            }
+            if (rv) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 s04 = *reinterpret_cast<const float4*>(sSig0 + lane * 20 + 4 * c4);
+                    const float s0v[4] = {s04.x, s04.y, s04.z, s04.w};
+                    float hv[8];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int c = 4 * c4 + kk;
+                        const float hx = fmaf(cW.w0c[2][c], S[c][1], -fmaf(cW.w0c[0][c], S[c][0], cW.w0c[4][c] * S[c][2]));
+                        const float hy = fmaf(cW.w0c[3][c], S[c][4], -fmaf(cW.w0c[1][c], S[c][3], cW.w0c[4][c] * S[c][5]));
+                        const float ox = fmaf(cW.w0c[0][c], sE[0], fmaf(cW.w0c[2][c], sE[1], cW.w0c[4][c] * sE[2]));
+                        const float oy = fmaf(cW.w0c[1][c], sE[3], fmaf(cW.w0c[3][c], sE[4], cW.w0c[4][c] * sE[5]));
+                        hv[2 * kk] = (hx - s0v[kk] * ox) * invn;
+                        hv[2 * kk + 1] = (hy - s0v[kk] * oy) * invn;
+                    }
+                    *reinterpret_cast<float4*>(sH + lane * 32 + 8 * c4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    *reinterpret_cast<float4*>(sH + lane * 32 + 8 * c4 + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---------------- Jacobian-side per-row contractions (FP32), rolled over groups of 4 input channels ----
+        //   WfS[c][a] = Wf[c][a] sigma1_i[c];  R = WfS W1c^T, T = WfS W1b^T, M = Wf^T + WfS W1a^T, Q = (M . sigma0) W0c^T
+        float Q[2][5];
+        {
+            float wfs[16][2];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 s14 = *reinterpret_cast<const float4*>(sS1 + kself * 20 + 4 * c4);
+                const float s1v[4] = {s14.x, s14.y, s14.z, s14.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    wfs[4 * c4 + kk][0] = cW.wf[4 * c4 + kk][0] * s1v[kk];
+                    wfs[4 * c4 + kk][1] = cW.wf[4 * c4 + kk][1] * s1v[kk];
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int f = 0; f < 5; ++f) Q[a][f] = 0.f;
+            __syncwarp();                    // every lane has read h (above) before the R|T rows overlay it
+#pragma unroll 1
+            for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 s04 = *reinterpret_cast<const float4*>(sSig0 + kself * 20 + 4 * e4);
+                const float s0v[4] = {s04.x, s04.y, s04.z, s04.w};
+                float r0v[4], r1v[4], t0v[4], t1v[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int e = 4 * e4 + kk;
+                    float r0 = 0.f, r1 = 0.f, t0 = 0.f, t1 = 0.f, mm0 = cW.wf[e][0], mm1 = cW.wf[e][1];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        r0 = fmaf(wfs[c][0], cW.w1c[e][c], r0); r1 = fmaf(wfs[c][1], cW.w1c[e][c], r1);
+                        t0 = fmaf(wfs[c][0], cW.w1b[e][c], t0); t1 = fmaf(wfs[c][1], cW.w1b[e][c], t1);
+                        mm0 = fmaf(wfs[c][0], cW.w1a[e][c], mm0); mm1 = fmaf(wfs[c][1], cW.w1a[e][c], mm1);
+                    }
+                    r0v[kk] = r0 * kLn2; r1v[kk] = r1 * kLn2;     // ln2: the pair pass uses Wt*log2e
+                    t0v[kk] = t0; t1v[kk] = t1;
+                    mm0 *= s0v[kk]; mm1 *= s0v[kk];
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) {
+                        Q[0][f] = fmaf(mm0, cW.w0c[f][e], Q[0][f]);
+                        Q[1][f] = fmaf(mm1, cW.w0c[f][e], Q[1][f]);
+                    }
+                }
+                if (rv) {
+                    float* sc = sScr + lane * 68 + 4 * e4;       // [R0 | R1 | T0 | T1] x 16
+                    *reinterpret_cast<float4*>(sc) = make_float4(r0v[0], r0v[1], r0v[2], r0v[3]);
+                    *reinterpret_cast<float4*>(sc + 16) = make_float4(r1v[0], r1v[1], r1v[2], r1v[3]);
+                    *reinterpret_cast<float4*>(sc + 32) = make_float4(t0v[0], t0v[1], t0v[2], t0v[3]);
+                    *reinterpret_cast<float4*>(sc + 48) = make_float4(t1v[0], t1v[1], t1v[2], t1v[3]);
+                }
+            }
+        }
+
+        // ---------------- pass 2 + 3: Jacobian blocks  J_ik = Q_i E_ik + R_i F_ik + T_i H_k  -> staging -----------
+        {
+            float R[2][16], T[2][16];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float* sc = sScr + kself * 68 + 4 * c4;
+                const float4 a0 = *reinterpret_cast<const float4*>(sc), a1 = *reinterpret_cast<const float4*>(sc + 16);
+                const float4 b0 = *reinterpret_cast<const float4*>(sc + 32), b1 = *reinterpret_cast<const float4*>(sc + 48);
+                R[0][4 * c4] = a0.x; R[0][4 * c4 + 1] = a0.y; R[0][4 * c4 + 2] = a0.z; R[0][4 * c4 + 3] = a0.w;
+                R[1][4 * c4] = a1.x; R[1][4 * c4 + 1] = a1.y; R[1][4 * c4 + 2] = a1.z; R[1][4 * c4 + 3] = a1.w;
+                T[0][4 * c4] = b0.x; T[0][4 * c4 + 1] = b0.y; T[0][4 * c4 + 2] = b0.z; T[0][4 * c4 + 3] = b0.w;
+                T[1][4 * c4] = b1.x; T[1][4 * c4 + 1] = b1.y; T[1][4 * c4 + 2] = b1.z; T[1][4 * c4 + 3] = b1.w;
+            }
+            __syncwarp();                    // all R|T rows are in registers before the J blocks overwrite the region
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+            float4 pn = sPos[0];
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                const float4 pj = pn;
+                pn = sPos[k + 1 < N ? k + 1 : k];
+                if (k != kself) {
+                    const WPairFeat f = wpair_features(pos, pj);
+                    const float i4d = 0.25f * rsqrt_approx(f.d2);
+                    // E_ik = (1/n) d t0_ik / d x_k   (5x2, 6 non-zeros)
+                    const float e0x = alpha * f.sx, e2x = -alpha * f.cx, e4x = -e0x * i4d;
+                    const float e1y = alpha * f.sy, e3y = -alpha * f.cy, e4y = -e1y * i4d;
+                    const float d = f.d2 * (4.f * i4d);
+                    float j00 = fmaf(Q[0][0], e0x, fmaf(Q[0][2], e2x, Q[0][4] * e4x));
+                    float j01 = fmaf(Q[0][1], e1y, fmaf(Q[0][3], e3y, Q[0][4] * e4y));
+                    float j10 = fmaf(Q[1][0], e0x, fmaf(Q[1][2], e2x, Q[1][4] * e4x));
+                    float j11 = fmaf(Q[1][1], e1y, fmaf(Q[1][3], e3y, Q[1][4] * e4y));
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
+                                        fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], cW.bt[c])))));
+                        const float sg = sigmoid2(a);
+                        // F_ik[c,:] = sigma_t * Wt^T E_ik   (Wt carries log2e; R carries ln2)
+                        const float fx = sg * fmaf(cW.wt[0][c], e0x, fmaf(cW.wt[2][c], e2x, cW.wt[4][c] * e4x));
+                        const float fy = sg * fmaf(cW.wt[1][c], e1y, fmaf(cW.wt[3][c], e3y, cW.wt[4][c] * e4y));
+                        j00 = fmaf(R[0][c], fx, j00); j01 = fmaf(R[0][c], fy, j01);
+                        j10 = fmaf(R[1][c], fx, j10); j11 = fmaf(R[1][c], fy, j11);
+                    }
+                    // mean-field coupling through hbar:  T_i H_k
+                    const float4* hk = reinterpret_cast<const float4*>(sH + k * 32);
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) {
+                        const float4 hv = hk[c2];
+                        j00 = fmaf(T[0][2 * c2], hv.x, fmaf(T[0][2 * c2 + 1], hv.z, j00));
+                        j01 = fmaf(T[0][2 * c2], hv.y, fmaf(T[0][2 * c2 + 1], hv.w, j01));
+                        j10 = fmaf(T[1][2 * c2], hv.x, fmaf(T[1][2 * c2 + 1], hv.z, j10));
+                        j11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, j11));
+                    }
+                    if (rv) sJ[lane * PB + k] = make_float4(j00, j01, j10, j11);
+                    rs0 += j00; rs1 += j01; rs2 += j10; rs3 += j11;
+                }
+            }
+            // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
+            if (rv) sJ[lane * PB + lane] = make_float4(1.f - rs0, -rs1, -rs2, 1.f - rs3);
+        }
+        __syncwarp();
+        if (p.out_jac && step == 0) {
+            float* oj = p.out_jac + (size_t)b * (2 * N) * (2 * N);
+            const float* Jf = reinterpret_cast<const float*>(sJ);
+            for (int q = lane; q < 4 * N * N; q += 32) {
+                const int rr = q / (2 * N), cc = q - rr * (2 * N);
+                oj[q] = Jf[((rr >> 1) * PB + (cc >> 1)) * 4 + (rr & 1) * 2 + (cc & 1)];
+            }
+        }
+
+        // ---------------- Jacobian LU: unpivoted 2x2-block LU, register-resident, rolled (shift-left) --------------
+        // Step k: every row eliminates the active block column (register 0) with the published pivot line k and
+        // -P_kk^{-1}, writing the updated block j into register j-1.  Row k+1, whose blocks are final after its
+        // update, inverts its new diagonal block right after the first update (the reciprocal chain overlaps the
+        // remaining updates) and publishes line k+1.  Rows <= k compute garbage nobody reads.
+        // log|det J| = sum_k log|det P_kk|.
+        float lacc = 0.f;                         // log2|det P_kk| of the pivot this lane owned
+        {
+            constexpr int LP = N + 4;
+            float4 Jr[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) Jr[j] = sJ[kself * PB + j];
+            bool bad = false;
+            float4* const line0 = reinterpret_cast<float4*>(sm + L_::o_H);      // [2][LP]: blocks 1..N-1, slot N = -P^{-1}, padding (prefetch)
+            auto inv_block = [&](const float4 pk) -> float4 {
+                const float det = pk.x * pk.w - pk.y * pk.z;
+                const float idet = rcp_approx(det);
+                lacc += lg2_approx(fabsf(det));
+                bad |= !(fabsf(det) > 0.05f);                               // also catches NaN
+                return make_float4(-pk.w * idet, pk.y * idet, pk.z * idet, -pk.x * idet);   // -P^{-1}
+            };
+            if (lane == 0) {
+                line0[N] = inv_block(Jr[0]);
+#pragma unroll
+                for (int j = 1; j < N; ++j) line0[j] = Jr[j];
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < N - 1; ++k) {
+                const float4* cur = line0 + (k & 1) * LP;
+                float4* nxt = line0 + ((k + 1) & 1) * LP;
+                const int lim = N - 1 - k;                                    // live trailing blocks: registers 1..lim
+                const bool act = rv && lane > k, pub = lane == k + 1;
+                const float4 m = cur[N];
+                const float4 a = Jr[0];
+                const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
+                const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
+                bad |= act && fmaxf(fmaxf(fabsf(l00), fabsf(l01)), fmaxf(fabsf(l10), fabsf(l11))) > 2.f;
+                float4 pa = cur[1], pb = cur[2];
+#pragma unroll
+                for (int j = 1; j < N; ++j) {
+                    if ((j & 1) && j > lim) break;                            // warp-uniform; at most one dead block of work
+                    const float4 pv = (j & 1) ? pa : pb;
+                    if (j & 1) pa = cur[j + 2]; else pb = cur[j + 2];         // two blocks ahead (padding makes it safe)
+                    float4 v = Jr[j];
+                    v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
+                    v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
+                    v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
+                    v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
+                    Jr[j - 1] = v;
+                    if (j == 1 && pub) nxt[N] = inv_block(v);
+                }
+                if (pub) {
+#pragma unroll
+                    for (int j = 1; j < N - 1; ++j) {
+                        if ((j & 3) == 1 && j >= lim) break;
+                        nxt[j] = Jr[j];
+                    }
+                }
+                __syncwarp();
+            }
+            bad = __any_sync(FULL, bad && rv) || (p.force_pivot != 0);
+            if (!rv) lacc = 0.f;
+            if (bad) {                              // rare: redo with the partially pivoted LU on the staged copy
+                lacc = pivoted_lu_smem<N>(reinterpret_cast<float*>(sJ), lane);     // all 32 lanes own scalar rows here
+                if (lane == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
+            }
+        }
+        __syncwarp();
+
+        // ---------------- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + dz/L --------------------
+        // (src/slater.py:14-17; the twist and any common displacement are pure row/column phases and drop out of
+        // |det|).  Lane r builds row r from per-particle power tables X_r^m, Y_r^m, m = 0..mmax (one sincospi per
+        // coordinate); for very large |m| the entries are computed directly and staged through shared memory.
+        double aD;
+        {
+            double2 Dr[N];
+            const double wx = fma(dzx, invL, ux), wy = fma(dzy, invL, uy);
+            if (mmax <= L_::MMAX_TAB) {
+                const int PT = (2 * (mmax + 1)) | 1;
+                double2* tb = sPt + kself * PT;
+                if (rv) {
+#pragma unroll 1
+                    for (int comp = 0; comp < 2; ++comp) {
+                        const double wv = comp ? wy : wx;
+                        double sn, cs;
+                        sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
+                        double2* t = tb + comp * (mmax + 1);
+                        double2 pw = make_double2(1.0, 0.0);
+                        t[0] = pw;
+                        for (int m = 1; m <= mmax; ++m) {
+                            pw = make_double2(pw.x * cs - pw.y * sn, pw.x * sn + pw.y * cs);
+                            t[m] = pw;
+                        }
+                    }
+                }
+                __syncwarp();
+                const double2* ty = tb + (mmax + 1);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const int2 mk = sK[j];
+                    double2 X = tb[abs(mk.x)], Y = ty[abs(mk.y)];
+                    X.y = mk.x < 0 ? -X.y : X.y;
+                    Y.y = mk.y < 0 ? -Y.y : Y.y;
+                    Dr[j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                }
+            } else {
+                double2* row = sPt + kself * PB;
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+                    const int2 mk = sK[j];
+                    double ph = fma((double)mk.x, wx, (double)mk.y * wy);
+                    ph -= rint(ph);
+                    double sn, cs;
+                    sincospi(2.0 * ph, &sn, &cs);
+                    if (rv) row[j] = make_double2(cs, sn);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < N; ++j) Dr[j] = row[j];
+            }
+            __syncwarp();     // H region (lines) free, tables read
+
+            // ---------------- Slater LU: partially pivoted, implicit row exchange, register-resident, rolled ---------
+            // Same shift-left scheme: the active column is register 0.  After its first update every unfinished
+            // row offers its new register 0; one REDUX picks the next pivot row, which publishes 1/pivot (the
+            // reciprocal chain overlaps the remaining updates) and then its row.  Finished rows compute garbage.
+            bool done = !rv, singular = false;
+            double mypn = 1.0, pncand = 1.0;
+            constexpr int LP = N + 4;
+            double2* const dline0 = reinterpret_cast<double2*>(sm + L_::o_H);    // [2][LP]
+            auto offer = [&](const double2 e) -> unsigned {
+                const float mag = (float)(fabs(e.x) + fabs(e.y));
+                const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x1Fu) | (unsigned)lane);
+                return __reduce_max_sync(FULL, key);
+            };
+            auto publish_inv = [&](const double2 e, double2* slot) {
+                const double pn = fma(e.x, e.x, e.y * e.y);
+                double ip = (double)rcp_approx((float)pn);                 // 1/pn: FP32 seed + 2 Newton steps
+                ip = ip * (2.0 - pn * ip);
+                ip = ip * (2.0 - pn * ip);
+                *slot = make_double2(e.x * ip, -e.y * ip);
+                pncand = pn;
+            };
+            unsigned wk = offer(Dr[0]);
+            if (!done && lane == (int)(wk & 31u) && (wk >> 5) != 0u) {
+                publish_inv(Dr[0], dline0 + N);
+#pragma unroll
+                for (int j = 1; j < N; ++j) dline0[j] = Dr[j];
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                const double2* cur = dline0 + (k & 1) * LP;
+                double2* nxt = dline0 + ((k + 1) & 1) * LP;
+                const int lim = N - 1 - k;
+                singular |= (wk >> 5) == 0u;
+                if (!done && lane == (int)(wk & 31u)) { done = true; mypn = pncand; }
+                if (lim == 0) break;
+                const double2 iv = cur[N];
+                const double2 c = Dr[0];
+                const double lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
+                const double ly = -(c.x * iv.y + c.y * iv.x);
+                bool win = false;
+                double2 pa = cur[1], pb = cur[2];
+#pragma unroll
+                for (int j = 1; j < N; ++j) {
+                    if ((j & 1) && j > lim) break;
+                    const double2 pv = (j & 1) ? pa : pb;
+                    if (j & 1) pa = cur[j + 2]; else pb = cur[j + 2];
+                    double2 v = Dr[j];
+                    v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                    v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                    Dr[j - 1] = v;
+                    if (j == 1) {
+                        wk = offer(v);
+                        win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
+                        if (win) publish_inv(v, nxt + N);
+                    }
+                }
+                if (win) {
+#pragma unroll
+                    for (int j = 1; j < N - 1; ++j) {
+                        if ((j & 3) == 1 && j >= lim) break;
+                        nxt[j] = Dr[j];
+                    }
+                }
+                __syncwarp();
+            }
+            aD = (rv && mypn != 1.0) ? 0.5 * log(mypn) : 0.0;
+            aD = warp_sum_f64(aD);
+            if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
+        }
+        const double aJ = warp_sum_f64((double)lacc * 0.693147180559945309417);
+
+        // ---------------- Metropolis accept / reject (MCMC.py:28-33), warp-uniform ------------------------------
+        const double ldD = aD - nlogL;
+        const double lp = 2.0 * ldD + aJ;                    // logpsi.py:30,179
+        int acc = 1;
+        if (step == 0) {
+            logp_cur = lp;
+            if (p.out_parts && lane == 0) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = aJ; }
+        } else {
+            double u;
+            if (p.uniforms) {
+                u = __ldg(p.uniforms + (size_t)(step - 1) * p.B + b);
+            } else {
+                const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, 0xffffffffu, 1u),
+                                               make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                u = ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
+            }
+            const double ratio = exp(lp - logp_cur);         // MCMC.py:28
+            acc = (u < ratio) ? 1 : 0;                       // MCMC.py:29  (NaN -> reject)
+            if (acc) logp_cur = lp;
+            if (p.out_acc_trace && lane == 0) p.out_acc_trace[(size_t)(step - 1) * p.B + b] = (uint8_t)acc;
+        }
+        if (p.out_logp_trace && lane == 0) p.out_logp_trace[(size_t)step * p.B + b] = lp;
+
+        const bool last = step == p.mc_steps;
+        if (p.mc_steps > 0) {
+            double2* xo = reinterpret_cast<double2*>(p.x_out + ((size_t)b * N + kself) * 2);
+            const bool changed = step == 0 ? (p.x_out != p.x) : (acc != 0);      // MCMC.py:31
+            if (last) {
+                double2 xf = xv;
+                if (!changed && rv) xf = __ldcg(xo);
+                if (p.wrap) { xf.x -= p.L * floor(xf.x / p.L); xf.y -= p.L * floor(xf.y / p.L); }   // VMC.py:24
+                if (rv) *xo = xf;
+            } else if (changed && rv) {
+                *xo = xv;
+            }
+        }
+        if (lane == 0) {
+            int na = 0;
+            if (step > 0) na = __ldcg(p.ws_nacc + b) + acc;
+            if (last) {
+                if (p.out_logp) p.out_logp[b] = logp_cur;
+                if (p.out_naccept) p.out_naccept[b] = na;
+            } else {
+                p.ws_logp[b] = logp_cur;
+                p.ws_nacc[b] = na;
+                p.done[b] = step + 1;
+            }
+        }
+        if (!last) {                       // publish the walker state, then push the walker back as ready
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned long long t = atomicAdd(p.qctr + 1, 1ull);
+                unsigned long long* slot = p.queue + (t & qmask);
+                while ((unsigned)(ld_acquire_u64(slot) >> 32) != (unsigned)t) __nanosleep(40);
+                st_release_u64(slot, ((unsigned long long)(unsigned)(t + 1ull) << 32) | (unsigned long long)(unsigned)b);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+bool wsweep_supported(int n) { return n == 13 || n == 29; }
+
+template <int N>
+static int launch_wn(const SweepParams& p, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // warps per CTA: 4 when the batch fills the machine, fewer for small batches so the walkers spread over all SMs
+    int wpc = 4;
+    while (wpc > 1 && (long long)p.B < (long long)sms * 3 * wpc) wpc >>= 1;
+    if (const char* s = getenv("CGB_W_WPC")) { const int v = atoi(s); if (v >= 1 && v <= 4) wpc = v; }   // tuning knobs
+    long long max_grid = 1ll << 40;
+    if (const char* s = getenv("CGB_W_GRID")) { const long long v = atoll(s); if (v >= 1) max_grid = v; }
+    const size_t smem = (size_t)WLay<N>::total * wpc;
+    cudaError_t e = cudaFuncSetAttribute(wsweep_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsweep_kernel<N>, wpc * 32, smem);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sms * occ;
+    const long long need = ((long long)p.B + wpc - 1) / wpc;      // never more warps than walkers
+    if (grid > need) grid = need;
+    if (grid > max_grid) grid = max_grid;
+    wsweep_kernel<N><<<(int)grid, wpc * 32, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
+    if (!wsweep_supported(p.n)) return CGB_E_UNSUPPORTED;
+    if ((unsigned long long)p.B * (unsigned long long)(p.mc_steps + 2) >= (1ull << 31)) return CGB_E_UNSUPPORTED;
+    prep_wconst_kernel<<<1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    // constant bank refresh, stream-ordered (device-to-device): calls on one stream are serialised by the stream;
+    // concurrent sweeps with DIFFERENT parameters on different streams of one device must be serialised by the caller.
+    e = cudaMemcpyToSymbolAsync(cW, wconst_staging, sizeof(WConst), 0, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    wqueue_init_kernel<<<(p.qcap + 255) / 256, 256, 0, st>>>(p.queue, (unsigned)p.qcap, (unsigned)p.B, p.qctr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(p.done, 0, sizeof(int) * (size_t)p.B, st);
+    if (e != cudaSuccess) return (int)e;
+    switch (p.n) {
+        case 13: return launch_wn<13>(p, st);
+        case 29: return launch_wn<29>(p, st);
+        default: return CGB_E_UNSUPPORTED;
+    }
+}
+
+}  // namespace cgb

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Share of executed warp instructions and of stall samples per kernel phase of cgb_sweep.cu, from an ncu
 report captured with --import-source on.  Phase boundaries are found from the "// ----------------" section
-comments of the source file.   usage: python tools/ncu_phases.py report.ncu-rep [evals]"""
+comments of the source file.   usage: python tools/ncu_phases.py report.ncu-rep [evals] [source file name]"""
 import csv, subprocess, sys, io, collections, os, re
 rep = sys.argv[1]
 evals = float(sys.argv[2]) if len(sys.argv) > 2 else None
-src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "coulombgas_b200", "csrc", "cgb_sweep.cu")
+srcname = sys.argv[3] if len(sys.argv) > 3 else "cgb_sweep.cu"
+src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "coulombgas_b200", "csrc", srcname)
 marks = []
 for ln, text in enumerate(open(src), 1):
     m = re.match(r"\s*// -{8,} ([^-:(]+)", text)
@@ -27,7 +28,7 @@ ti = sum(f(r, "Instructions Executed") for _, r in recs); ts = sum(f(r, "# Sampl
 agg = collections.OrderedDict([("setup", [0, 0])] + [(m[1], [0, 0]) for m in marks] + [("helpers/inlined", [0, 0])])
 for fn, r in recs:
     ln = int(r[0]); ie = f(r, "Instructions Executed"); sm = f(r, "# Samples")
-    if fn == "cgb_sweep.cu" and ln >= kstart:
+    if fn == srcname and ln >= kstart:
         name = "setup"
         for a, nm in marks:
             if ln >= a: name = nm
