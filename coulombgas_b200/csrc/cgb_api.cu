@@ -98,6 +98,7 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     p.force_pivot = (fp && fp[0] == '1') ? 1 : 0;
     char* ws = (char*)workspace;
     p.fallback_counter = (unsigned long long*)(ws + WS_CTR);
+    p.wconst = ws + WS_WCONST;
     p.qctr = (unsigned long long*)(ws + WS_CTR + 64);
     p.qcap = ws_qcap(B);
     p.queue = (unsigned long long*)(ws + WS_DYN);

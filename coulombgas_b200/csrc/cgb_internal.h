@@ -46,6 +46,7 @@ struct SweepParams {
     int force_pivot;          // debug: always use the pivoted scalar LU for the Jacobian
     unsigned long long* fallback_counter;   // evaluations redone with the pivoted LU (in the workspace)
     // ---- warp-per-walker kernel only (cgb_wsweep.cu): per-call scheduler state in the caller's workspace
+    const void* wconst;           // staging copy of the constant-bank weight block (device)
     unsigned long long* qctr;     // [0] queue head, [1] queue tail, [2] spin diagnostics (initialised per call)
     unsigned long long* queue;    // (qcap) ready-queue slots
     unsigned qcap;                // power of two >= 2*B

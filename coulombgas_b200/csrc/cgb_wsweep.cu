@@ -94,7 +94,7 @@ struct WLay {
     static constexpr int RJ = ((J_bytes > alias_bytes ? J_bytes : alias_bytes) + 15) & ~15;
     static constexpr int o_J = 0;
     static constexpr int o_H = RJ;                        // float[N][16][2] H_k; afterwards the LU pivot lines
-    static constexpr int H_bytes = 128 * N > 32 * (N + 4) ? 128 * N : 32 * (N + 4);
+    static constexpr int H_bytes = 128 * N > 32 * (N + 8) ? 128 * N : 32 * (N + 8);
     static constexpr int o_pos = o_H + H_bytes;           // float4[N] half-angle table
     static constexpr int o_k = o_pos + 16 * N;            // int2[N]   integer part of the occupied k rows
     static constexpr int total = (o_k + 8 * N + 15) & ~15;
@@ -223,6 +223,16 @@ __global__ void wqueue_init_kernel(unsigned long long* slots, unsigned cap, unsi
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-shared float64 weights of the forward single-particle stream, regrouped [c4][e][kk] (output channel c = 4 c4 + kk)
+// so that one group of 4 output channels reads contiguous 32-byte rows by broadcast LDS.128.  (As runtime-indexed
+// constant-bank loads these 8 kB thrashed the constant cache: 16 % of all stall samples on 2 % of the instructions.)
+struct WShared {
+    double w1a[4][16][4];
+    double w1c[4][16][4];
+    double w0c[4][5][4];
+};
+constexpr int W_SHARED_BYTES = (sizeof(WShared) + 15) & ~15;
+
 template <int N>
 __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -230,7 +240,21 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int PB = L_::PB;
     const int lane = threadIdx.x & 31;
-    unsigned char* sm = smem_raw + (threadIdx.x >> 5) * L_::total;
+    WShared* const sW = reinterpret_cast<WShared*>(smem_raw);
+    {
+        const WConst* wc = reinterpret_cast<const WConst*>(p.wconst);
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+            const int e = t >> 4, c = t & 15;
+            sW->w1a[c >> 2][e][c & 3] = wc->dw1a[e][c];
+            sW->w1c[c >> 2][e][c & 3] = wc->dw1c[e][c];
+        }
+        for (int t = threadIdx.x; t < 80; t += blockDim.x) {
+            const int f = t >> 4, c = t & 15;
+            sW->w0c[c >> 2][f][c & 3] = wc->dw0c[f][c];
+        }
+        __syncthreads();                  // the only block barrier: before the warps go their own ways
+    }
+    unsigned char* sm = smem_raw + W_SHARED_BYTES + (threadIdx.x >> 5) * L_::total;
     float4* const sJ = reinterpret_cast<float4*>(sm + L_::o_J);
     float* const sSig0 = reinterpret_cast<float*>(sm + L_::a_sig0);
     double* const sHbuf = reinterpret_cast<double*>(sm + L_::a_hbuf);
@@ -368,13 +392,18 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 double hq[4];
                 float sq[4];
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int c = 4 * c4 + kk;
-                    double pre = cW.db0[c];
+                double pre[4];
 #pragma unroll
-                    for (int f = 0; f < 5; ++f) pre = fma(m0d[f], cW.dw0c[f][c], pre);
-                    softplus_sigmoid_f64w(pre, hq[kk], sq[kk]);
+                for (int kk = 0; kk < 4; ++kk) pre[kk] = cW.db0[4 * c4 + kk];
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    const double2 wa = *reinterpret_cast<const double2*>(&sW->w0c[c4][f][0]);
+                    const double2 wb = *reinterpret_cast<const double2*>(&sW->w0c[c4][f][2]);
+                    pre[0] = fma(m0d[f], wa.x, pre[0]); pre[1] = fma(m0d[f], wa.y, pre[1]);
+                    pre[2] = fma(m0d[f], wb.x, pre[2]); pre[3] = fma(m0d[f], wb.y, pre[3]);
                 }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) softplus_sigmoid_f64w(pre[kk], hq[kk], sq[kk]);
                 if (rv) {
                     *reinterpret_cast<float4*>(sSig0 + lane * 20 + 4 * c4) = make_float4(sq[0], sq[1], sq[2], sq[3]);
 #pragma unroll
@@ -403,18 +432,25 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
                 float sq[4];
+                double ga[4], gm[4];              // two accumulation chains per channel (h part, mean-t part)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { ga[kk] = cW.db1[4 * c4 + kk] + sGb[4 * c4 + kk]; gm[kk] = 0.0; }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(&sW->w1a[c4][e][0]);
+                    const double2 a23 = *reinterpret_cast<const double2*>(&sW->w1a[c4][e][2]);
+                    const double2 c01 = *reinterpret_cast<const double2*>(&sW->w1c[c4][e][0]);
+                    const double2 c23 = *reinterpret_cast<const double2*>(&sW->w1c[c4][e][2]);
+                    ga[0] = fma(h[e], a01.x, ga[0]); ga[1] = fma(h[e], a01.y, ga[1]);
+                    ga[2] = fma(h[e], a23.x, ga[2]); ga[3] = fma(h[e], a23.y, ga[3]);
+                    gm[0] = fma(md[e], c01.x, gm[0]); gm[1] = fma(md[e], c01.y, gm[1]);
+                    gm[2] = fma(md[e], c23.x, gm[2]); gm[3] = fma(md[e], c23.y, gm[3]);
+                }
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const int c = 4 * c4 + kk;
-                    double g0 = cW.db1[c] + sGb[c], g1 = 0.0, g2 = 0.0, g3 = 0.0;    // 4 chains per channel: DFMA latency
-#pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        g0 = fma(h[e], cW.dw1a[e][c], g0); g1 = fma(md[e], cW.dw1c[e][c], g1);
-                        g2 = fma(h[e + 1], cW.dw1a[e + 1][c], g2); g3 = fma(md[e + 1], cW.dw1c[e + 1][c], g3);
-                    }
-                    const double g = (g0 + g1) + (g2 + g3);
                     double sp;
-                    softplus_sigmoid_f64w(g, sp, sq[kk]);
+                    softplus_sigmoid_f64w(ga[kk] + gm[kk], sp, sq[kk]);
                     const double sv = sHbuf[kself * 17 + c] + sp;  // s_i (flow.py:52)
                     dzx = fma(sv, cW.dwf[c][0], dzx);
                     dzy = fma(sv, cW.dwf[c][1], dzy);
@@ -612,7 +648,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
         // log|det J| = sum_k log|det P_kk|.
         float lacc = 0.f;                         // log2|det P_kk| of the pivot this lane owned
         {
-            constexpr int LP = N + 4;
+            constexpr int LP = N + 8;
             float4 Jr[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) Jr[j] = sJ[kself * PB + j];
@@ -642,19 +678,29 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
                 const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
                 bad |= act && fmaxf(fmaxf(fabsf(l00), fabsf(l01)), fmaxf(fabsf(l10), fabsf(l11))) > 2.f;
-                float4 pa = cur[1], pb = cur[2];
+                float4 pq[4] = {cur[1], cur[2], cur[3], cur[4]};
 #pragma unroll
-                for (int j = 1; j < N; ++j) {
-                    if ((j & 1) && j > lim) break;                            // warp-uniform; at most one dead block of work
-                    const float4 pv = (j & 1) ? pa : pb;
-                    if (j & 1) pa = cur[j + 2]; else pb = cur[j + 2];         // two blocks ahead (padding makes it safe)
-                    float4 v = Jr[j];
-                    v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
-                    v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
-                    v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
-                    v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
-                    Jr[j - 1] = v;
-                    if (j == 1 && pub) nxt[N] = inv_block(v);
+                for (int j0 = 1; j0 < N; j0 += 4) {
+                    if (j0 > lim) break;                                      // warp-uniform; at most three dead blocks of work
+                    float4 nq[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) nq[t] = cur[j0 + 4 + t];      // next chunk ahead of its use (line is padded)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = j0 + t;
+                        if (j < N) {
+                            const float4 pv = pq[t];
+                            float4 v = Jr[j];
+                            v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
+                            v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
+                            v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
+                            v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
+                            Jr[j - 1] = v;
+                            if (j == 1 && pub) nxt[N] = inv_block(v);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) pq[t] = nq[t];
                 }
                 if (pub) {
 #pragma unroll
@@ -733,7 +779,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
             // reciprocal chain overlaps the remaining updates) and then its row.  Finished rows compute garbage.
             bool done = !rv, singular = false;
             double mypn = 1.0, pncand = 1.0;
-            constexpr int LP = N + 4;
+            constexpr int LP = N + 8;
             double2* const dline0 = reinterpret_cast<double2*>(sm + L_::o_H);    // [2][LP]
             auto offer = [&](const double2 e) -> unsigned {
                 const float mag = (float)(fabs(e.x) + fabs(e.y));
@@ -768,21 +814,36 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 const double lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
                 const double ly = -(c.x * iv.y + c.y * iv.x);
                 bool win = false;
-                double2 pa = cur[1], pb = cur[2];
+                double2 pq[4] = {cur[1], cur[2], cur[3], cur[4]};
 #pragma unroll
-                for (int j = 1; j < N; ++j) {
-                    if ((j & 1) && j > lim) break;
-                    const double2 pv = (j & 1) ? pa : pb;
-                    if (j & 1) pa = cur[j + 2]; else pb = cur[j + 2];
-                    double2 v = Dr[j];
-                    v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
-                    v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                    Dr[j - 1] = v;
-                    if (j == 1) {
-                        wk = offer(v);
-                        win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
-                        if (win) publish_inv(v, nxt + N);
+                for (int j0 = 1; j0 < N; j0 += 4) {
+                    if (j0 > lim) break;
+                    double2 nq[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) nq[t] = cur[j0 + 4 + t];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)                               // independent first halves (written straight to the
+                        if (j0 + t < N) {                                     // shifted slot): covers the DFMA latency
+                            const double2 o = Dr[j0 + t];
+                            Dr[j0 + t - 1] = make_double2(fma(-ly, pq[t].y, o.x), fma(ly, pq[t].x, o.y));
+                        }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = j0 + t;
+                        if (j < N) {
+                            double2 v = Dr[j - 1];
+                            v.x = fma(lx, pq[t].x, v.x);
+                            v.y = fma(lx, pq[t].y, v.y);
+                            Dr[j - 1] = v;
+                            if (j == 1) {
+                                wk = offer(v);
+                                win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
+                                if (win) publish_inv(v, nxt + N);
+                            }
+                        }
                     }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) pq[t] = nq[t];
                 }
                 if (win) {
 #pragma unroll
@@ -874,7 +935,7 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     if (const char* s = getenv("CGB_W_WPC")) { const int v = atoi(s); if (v >= 1 && v <= 4) wpc = v; }   // tuning knobs
     long long max_grid = 1ll << 40;
     if (const char* s = getenv("CGB_W_GRID")) { const long long v = atoll(s); if (v >= 1) max_grid = v; }
-    const size_t smem = (size_t)WLay<N>::total * wpc;
+    const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * wpc;
     cudaError_t e = cudaFuncSetAttribute(wsweep_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int occ = 1;
@@ -891,6 +952,7 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
 int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
     if (!wsweep_supported(p.n)) return CGB_E_UNSUPPORTED;
     if ((unsigned long long)p.B * (unsigned long long)(p.mc_steps + 2) >= (1ull << 31)) return CGB_E_UNSUPPORTED;
+    if (p.wconst != wconst_staging) return CGB_E_BADARG;
     prep_wconst_kernel<<<1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
