@@ -133,7 +133,7 @@ def run_reference(args):
     c, x, si = load_inputs(256)
     from oracle import tables
     G = tables.kpoints(2, CFG["Gmax"])
-    walkers, sub_steps = 32, 2
+    walkers, sub_steps = 128, 3
     vals, secs = [], []
     for it in range(args.warmup + args.steps):
         v, ew, s = cpu_reference_rate(c, x, si, G, walkers, sub_steps, threads)
@@ -241,6 +241,13 @@ def main():
     mufu = max(8 * 20000 * blocks * 256 / cg.microbench(1, blocks, 20000) for _ in range(3)) / 1e12
     flop = cg.flops.flop_sweep(n, S) * B
     achieved = flop / (ms_sweep * 1e-3) / 1e12
+    # DRAM traffic of one sweep launch at this shape, from the committed ncu --set full capture (profiles/)
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
+    if os.path.exists(tfile):
+        tj = json.load(open(tfile))
+        if tj.get("batch") == B and tj.get("mc_steps") == S:
+            traffic = tj.get("dram_bytes_per_launch")
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
 
@@ -288,10 +295,10 @@ def main():
         "sweep_kernel_ms": ms_sweep, "ewald_kernel_ms": ms_ewald,
         "accept_rate": float(acc), "V_mean_over_rs2": float(vm) / c["rs"] ** 2,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 4 * args.steps,      # per step: prep_wconst + wqueue_init + wsweep_kernel<29> + ewald_kernel
         "clocks": clocks,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
-                     "traffic": None, "kernel": "sweep_kernel<4>",
+                     "traffic": traffic, "kernel": "wsweep_kernel<29>",
                      "note": "compute-bound path (>2000 FLOP/B): achieved = (8n^3+895n^2+1760n)*(mc_steps+1)*B algorithmic "
                              "FLOP / CUDA-event kernel time; peak = FFMA-saturating micro-kernel measured in this run "
                              "(MEASURED_PEAKS.json has only HBM %s GB/s and bf16); MUFU peak %.2f Top/s"
@@ -302,9 +309,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             from oracle import tables
-            v, ew, secs = cpu_reference_rate(c, x_host, si_host, tables.kpoints(2, CFG["Gmax"]), 64, 3, threads)
+            v, ew, secs = cpu_reference_rate(c, x_host, si_host, tables.kpoints(2, CFG["Gmax"]), 256, 7, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "64 walkers x (3 proposals + initial log p) + Ewald, scaled to the 50-proposal "
+                                    "sample": "256 walkers x (7 proposals + initial log p) + Ewald, scaled to the 50-proposal "
                                               "sweep; restated reference algorithm (torch-f64 vmap+jacfwd+LAPACK), %.1f s" % secs,
                                     "ewald_evals_per_sec": ew}
         print(json.dumps(line), flush=True)

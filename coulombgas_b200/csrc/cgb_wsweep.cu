@@ -239,9 +239,13 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
     using L_ = WLay<N>;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int PB = L_::PB;
-    const int lane = threadIdx.x & 31;
-    WShared* const sW = reinterpret_cast<WShared*>(smem_raw);
+    // lane id and the warp's slice offset pass through volatile asm so that the compiler keeps them in registers:
+    // otherwise, at the 168-register cap, it re-derives them from S2R (tid, shared-window base) inside the hot loops.
+    // (a plain mov is still rematerialised by ptxas; the result of a shuffle is not)
+    const int lane = __shfl_sync(0xffffffffu, (int)(threadIdx.x & 31), (int)(threadIdx.x & 31));
+    const int wofs = __shfl_sync(0xffffffffu, (int)(W_SHARED_BYTES + (threadIdx.x >> 5) * L_::total), 0);
     {
+        WShared* const sW = reinterpret_cast<WShared*>(smem_raw);
         const WConst* wc = reinterpret_cast<const WConst*>(p.wconst);
         for (int t = threadIdx.x; t < 256; t += blockDim.x) {
             const int e = t >> 4, c = t & 15;
@@ -254,7 +258,11 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
         }
         __syncthreads();                  // the only block barrier: before the warps go their own ways
     }
-    unsigned char* sm = smem_raw + W_SHARED_BYTES + (threadIdx.x >> 5) * L_::total;
+    // the slice base as a pinned 32-bit shared-window address (the window base is a function of %cluster_ctarank that
+    // the compiler otherwise re-derives with S2UR + ULEA at every use site)
+    const unsigned sbase32 = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)wofs, 0);
+    unsigned char* sm = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic((size_t)sbase32));
+    const WShared* const sW = reinterpret_cast<const WShared*>(__cvta_shared_to_generic((size_t)(sbase32 - (unsigned)wofs)));
     float4* const sJ = reinterpret_cast<float4*>(sm + L_::o_J);
     float* const sSig0 = reinterpret_cast<float*>(sm + L_::a_sig0);
     double* const sHbuf = reinterpret_cast<double*>(sm + L_::a_hbuf);
@@ -358,32 +366,44 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
         {
             double md[16], m0d[5];
             {
-                float m[16], mc[16], m0[5], m0c[5];
+                // sum_k softplus2(a_k) = 1/2 (sum_k a_k + sum_k |a_k|) + log2 prod_k (1 + 2^-|a_k|):
+                //   sum_k a_k follows from the feature sums (linear), sum_k |a_k| is accumulated in float64, and the product
+                //   (29 factors in (1,2]) is one FFMA per term -- ONE logarithm per channel and evaluation instead of 29.
+                double sab[16], m0s[5];
+                float P[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) { m[c] = 0.f; mc[c] = 0.f; }
+                for (int c = 0; c < 16; ++c) { sab[c] = 0.0; P[c] = 1.f; }
 #pragma unroll
-                for (int f = 0; f < 5; ++f) { m0[f] = 0.f; m0c[f] = 0.f; }
+                for (int f = 0; f < 5; ++f) m0s[f] = 0.0;
                 float4 pn = sPos[0];
 #pragma unroll 1
                 for (int k = 0; k < N; ++k) {
                     const WPairFeat f = wpair_features(pos, pn);
                     pn = sPos[k + 1 < N ? k + 1 : k];             // next partner's table entry ahead of its use
                     const float d = sqrt_approx(f.d2);            // 0 on the diagonal (flow.py:25)
-                    kahan_add_w(m0[0], m0c[0], f.cx); kahan_add_w(m0[1], m0c[1], f.cy);
-                    kahan_add_w(m0[2], m0c[2], f.sx); kahan_add_w(m0[3], m0c[3], f.sy);
-                    kahan_add_w(m0[4], m0c[4], d);
+                    m0s[0] += (double)f.cx; m0s[1] += (double)f.cy; m0s[2] += (double)f.sx; m0s[3] += (double)f.sy;
+                    m0s[4] += (double)d;
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
                         const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
                                         fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], cW.bt[c])))));
-                        kahan_add_w(m[c], mc[c], softplus2(a));
+                        sab[c] += (double)fabsf(a);
+                        P[c] = fmaf(P[c], ex2_approx(-fabsf(a)), P[c]);
                     }
                 }
                 const double invnd = 1.0 / (double)N;
 #pragma unroll
-                for (int f = 0; f < 5; ++f) m0d[f] = ((double)m0[f] - (double)m0c[f]) * invnd;
+                for (int f = 0; f < 5; ++f) m0d[f] = m0s[f] * invnd;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) md[c] = ((double)m[c] - (double)mc[c]) * (0.693147180559945309417 * invnd);
+                for (int c = 0; c < 16; ++c) {
+                    double sa = (double)N * (double)cW.bt[c];
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) sa = fma(m0s[f], (double)cW.wt[f][c], sa);
+                    const int pb = __float_as_int(P[c]);
+                    const float mant = __int_as_float((pb & 0x007fffff) | 0x3f800000);         // P = 2^ex * mant, mant in [1,2)
+                    const double lg = (double)((pb >> 23) - 127) + (double)lg2_approx(mant);   // abs error 2^-22 on a sum ~ n
+                    md[c] = (0.5 * (sa + sab[c]) + lg) * (0.693147180559945309417 * invnd);
+                }
             }
             // ---------------- single-particle stream (flow.py:45,51-55): forward values in float64 -----------
             // rolled over groups of 4 output channels (uniform constant-bank indices)
