@@ -375,8 +375,11 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 for (int c = 0; c < 16; ++c) { sab[c] = 0.0; P[c] = 1.f; }
 #pragma unroll
                 for (int f = 0; f < 5; ++f) m0s[f] = 0.0;
+                float btr[16];                                    // biases in registers (an FFMA takes one constant operand)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) btr[c] = cW.bt[c];
                 float4 pn = sPos[0];
-#pragma unroll 1
+#pragma unroll 2
                 for (int k = 0; k < N; ++k) {
                     const WPairFeat f = wpair_features(pos, pn);
                     pn = sPos[k + 1 < N ? k + 1 : k];             // next partner's table entry ahead of its use
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
                         const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
-                                        fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], cW.bt[c])))));
+                                        fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], btr[c])))));
                         sab[c] += (double)fabsf(a);
                         P[c] = fmaf(P[c], ex2_approx(-fabsf(a)), P[c]);
                     }
@@ -481,40 +484,74 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
         __syncwarp();
 
         // ---------------- pass 2b: H_i = d hbar / d x_i = (1/n) [ sum_k P_k E_ki - P_i sum_k E_ik ] ------------
-        // P_k E_ki = sigma0_k . W0c^T (eps . E_ik), eps = (-,-,+,+,-): accumulate S[c][fd] = sum_k sigma0_k[c] E_ik[fd]
-        // over the 6 non-zero entries fd of E (96 FMA per pair) and contract with W0c once at the end.
+        // P_k E_ki = sigma0_k . W0c^T (eps . E_ik), eps = (-,-,+,+,-), so H needs S[c][fd] = sum_{k!=i} sigma0_k[c] E_ik[fd] for
+        // the 6 non-zero entries fd of E.  Four of them are cos/sin of theta_i - theta_k and SEPARATE:
+        //   sum_k s0_k[c] sin(th_i - th_k) = sin th_i (sum_k s0_k[c] cos th_k) - cos th_i (sum_k s0_k[c] sin th_k),
+        // i.e. O(n) work from 68 warp-wide sums (A/B per channel and direction, plus the plain sums for sum_k E_ik);
+        // only the two d-feature entries (-alpha sin(th)/(4 d_ik)) need the pair loop: 32 FMA per pair instead of 96.
         {
-            float S[16][6];
+            const float cthx = fmaf(-2.f * pos.y, pos.y, 1.f), sthx = 2.f * pos.y * pos.x;     // full angles 2 pi u
+            const float cthy = fmaf(-2.f * pos.w, pos.w, 1.f), sthy = 2.f * pos.w * pos.z;
+            float* const sTab = sScr;                 // [N][68] contributions, then [68] sums at row 0 (h is dead: region free)
+            if (rv) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 s04 = *reinterpret_cast<const float4*>(sSig0 + lane * 20 + 4 * c4);
+                    const float s0v[4] = {s04.x, s04.y, s04.z, s04.w};
 #pragma unroll
-                for (int q = 0; q < 6; ++q) S[c][q] = 0.f;
-            float sE[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // sum_k E_ik : (0x,2x,4x,1y,3y,4y)
+                    for (int kk = 0; kk < 4; ++kk)
+                        *reinterpret_cast<float4*>(sTab + lane * 68 + 4 * (4 * c4 + kk)) =
+                            make_float4(s0v[kk] * cthx, s0v[kk] * sthx, s0v[kk] * cthy, s0v[kk] * sthy);
+                }
+                *reinterpret_cast<float4*>(sTab + lane * 68 + 64) = make_float4(cthx, sthx, cthy, sthy);
+            }
+            __syncwarp();
+            float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f;    // column sums: columns lane, lane+32, lane+64 (< 68)
+            {
+                const int c2 = lane + 64 < 68 ? lane + 64 : 64;
+#pragma unroll 4
+                for (int r = 0; r < N; ++r) {
+                    cs0 += sTab[r * 68 + lane]; cs1 += sTab[r * 68 + 32 + lane]; cs2 += sTab[r * 68 + c2];
+                }
+            }
+            __syncwarp();
+            float* const sSum = sTab + N * 68 - 68;   // last row slot is rewritten with the sums (row N-1 already consumed)
+            sSum[lane] = cs0; sSum[32 + lane] = cs1;
+            if (lane < 4) sSum[64 + lane] = cs2;
+            __syncwarp();
+
+            float S4[16][2];                          // pairwise part: fd = 4x, 4y
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { S4[c][0] = 0.f; S4[c][1] = 0.f; }
+            float sE4x = 0.f, sE4y = 0.f;
             float4 pn = sPos[0];
-#pragma unroll 1
+#pragma unroll 2
             for (int k = 0; k < N; ++k) {
                 const float4 pj = pn;
                 pn = sPos[k + 1 < N ? k + 1 : k];
                 if (k != kself) {
-                    const WPairFeat f = wpair_features(pos, pj);
-                    const float i4d = 0.25f * rsqrt_approx(f.d2);
-                    float E[6];
-                    E[0] = alpha * f.sx; E[1] = -alpha * f.cx; E[2] = -E[0] * i4d;
-                    E[3] = alpha * f.sy; E[4] = -alpha * f.cy; E[5] = -E[3] * i4d;
+                    const float shx = pos.y * pj.x - pos.x * pj.y, chx = fmaf(pos.x, pj.x, pos.y * pj.y);
+                    const float shy = pos.w * pj.z - pos.z * pj.w, chy = fmaf(pos.z, pj.z, pos.w * pj.w);
+                    const float ai4d = (-0.5f * alpha) * rsqrt_approx(fmaf(shx, shx, shy * shy));     // -alpha / (4 d) * 2
+                    const float e4x = shx * chx * ai4d, e4y = shy * chy * ai4d;                        // -alpha sin(th)/(4 d)
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const float4 sk4 = *reinterpret_cast<const float4*>(sSig0 + k * 20 + 4 * c4);
                         const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                            for (int q = 0; q < 6; ++q) S[4 * c4 + kk][q] = fmaf(skv[kk], E[q], S[4 * c4 + kk][q]);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            S4[4 * c4 + kk][0] = fmaf(skv[kk], e4x, S4[4 * c4 + kk][0]);
+                            S4[4 * c4 + kk][1] = fmaf(skv[kk], e4y, S4[4 * c4 + kk][1]);
+                        }
                     }
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) sE[q] += E[q];
+                    sE4x += e4x; sE4y += e4y;
                 }
             }
             if (rv) {
+                const float4 tot = *reinterpret_cast<const float4*>(sSum + 64);            // sum_k (cos thx, sin thx, cos thy, sin thy)
+                // sum_{k != i} E_ik:  (0x, 2x, 1y, 3y); the k = i term of cos(0) = 1 is taken out
+                const float sE0 = alpha * (sthx * tot.x - cthx * tot.y), sE1 = alpha - alpha * (cthx * tot.x + sthx * tot.y);
+                const float sE3 = alpha * (sthy * tot.z - cthy * tot.w), sE4 = alpha - alpha * (cthy * tot.z + sthy * tot.w);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const float4 s04 = *reinterpret_cast<const float4*>(sSig0 + lane * 20 + 4 * c4);
@@ -523,10 +560,15 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const int c = 4 * c4 + kk;
-                        const float hx = fmaf(cW.w0c[2][c], S[c][1], -fmaf(cW.w0c[0][c], S[c][0], cW.w0c[4][c] * S[c][2]));
-                        const float hy = fmaf(cW.w0c[3][c], S[c][4], -fmaf(cW.w0c[1][c], S[c][3], cW.w0c[4][c] * S[c][5]));
-                        const float ox = fmaf(cW.w0c[0][c], sE[0], fmaf(cW.w0c[2][c], sE[1], cW.w0c[4][c] * sE[2]));
-                        const float oy = fmaf(cW.w0c[1][c], sE[3], fmaf(cW.w0c[3][c], sE[4], cW.w0c[4][c] * sE[5]));
+                        const float4 ab = *reinterpret_cast<const float4*>(sSum + 4 * c);     // (Ax, Bx, Ay, By)[c]
+                        const float S0 = alpha * (sthx * ab.x - cthx * ab.y);
+                        const float S1 = alpha * s0v[kk] - alpha * (cthx * ab.x + sthx * ab.y);
+                        const float S3 = alpha * (sthy * ab.z - cthy * ab.w);
+                        const float S4v = alpha * s0v[kk] - alpha * (cthy * ab.z + sthy * ab.w);
+                        const float hx = fmaf(cW.w0c[2][c], S1, -fmaf(cW.w0c[0][c], S0, cW.w0c[4][c] * S4[c][0]));
+                        const float hy = fmaf(cW.w0c[3][c], S4v, -fmaf(cW.w0c[1][c], S3, cW.w0c[4][c] * S4[c][1]));
+                        const float ox = fmaf(cW.w0c[0][c], sE0, fmaf(cW.w0c[2][c], sE1, cW.w0c[4][c] * sE4x));
+                        const float oy = fmaf(cW.w0c[1][c], sE3, fmaf(cW.w0c[3][c], sE4, cW.w0c[4][c] * sE4y));
                         hv[2 * kk] = (hx - s0v[kk] * ox) * invn;
                         hv[2 * kk + 1] = (hy - s0v[kk] * oy) * invn;
                     }
