@@ -112,6 +112,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ float4 shfl4w(const float4 v, int src) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+__device__ __forceinline__ double2 shfl2dw(const double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -704,27 +711,28 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
 
         // ---------------- Jacobian LU: unpivoted 2x2-block LU, register-resident, rolled (shift-left) --------------
         // Step k: every row eliminates the active block column (register 0) with the published pivot line k and
-        // -P_kk^{-1}, writing the updated block j into register j-1.  Row k+1, whose blocks are final after its
-        // update, inverts its new diagonal block right after the first update (the reciprocal chain overlaps the
-        // remaining updates) and publishes line k+1.  Rows <= k compute garbage nobody reads.
-        // log|det J| = sum_k log|det P_kk|.
-        float lacc = 0.f;                         // log2|det P_kk| of the pivot this lane owned
+        // -P_kk^{-1}, writing the updated block j into register j-1.  Right after the first update the new diagonal
+        // block of row k+1 is broadcast by shuffle and EVERY lane inverts it (no divergent branch: the reciprocal
+        // chain interleaves with the remaining updates instead of serialising the warp); row k+1 then publishes
+        // its row as line k+1.  Rows <= k compute garbage nobody reads.  log|det J| = sum_k log|det P_kk|.
+        float lacc = 0.f;                         // sum_k log2|det P_kk|, identical in every lane
+        bool lacc_per_lane = false;               // pivoted fallback: per-lane partial sums instead
         {
             constexpr int LP = N + 8;
             float4 Jr[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) Jr[j] = sJ[kself * PB + j];
             bool bad = false;
-            float4* const line0 = reinterpret_cast<float4*>(sm + L_::o_H);      // [2][LP]: blocks 1..N-1, slot N = -P^{-1}, padding (prefetch)
-            auto inv_block = [&](const float4 pk) -> float4 {
+            float4* const line0 = reinterpret_cast<float4*>(sm + L_::o_H);      // [2][LP]: blocks 1..N-1 (+ prefetch padding)
+            auto neg_inv = [&](const float4 pk) -> float4 {
                 const float det = pk.x * pk.w - pk.y * pk.z;
                 const float idet = rcp_approx(det);
                 lacc += lg2_approx(fabsf(det));
                 bad |= !(fabsf(det) > 0.05f);                               // also catches NaN
                 return make_float4(-pk.w * idet, pk.y * idet, pk.z * idet, -pk.x * idet);   // -P^{-1}
             };
+            float4 m = neg_inv(shfl4w(Jr[0], 0));
             if (lane == 0) {
-                line0[N] = inv_block(Jr[0]);
 #pragma unroll
                 for (int j = 1; j < N; ++j) line0[j] = Jr[j];
             }
@@ -734,8 +742,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 const float4* cur = line0 + (k & 1) * LP;
                 float4* nxt = line0 + ((k + 1) & 1) * LP;
                 const int lim = N - 1 - k;                                    // live trailing blocks: registers 1..lim
-                const bool act = rv && lane > k, pub = lane == k + 1;
-                const float4 m = cur[N];
+                const bool act = rv && lane > k;
                 const float4 a = Jr[0];
                 const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
                 const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
@@ -758,13 +765,13 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                             v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
                             v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
                             Jr[j - 1] = v;
-                            if (j == 1 && pub) nxt[N] = inv_block(v);
+                            if (j == 1) m = neg_inv(shfl4w(v, k + 1));        // next pivot block, inverted by every lane
                         }
                     }
 #pragma unroll
                     for (int t = 0; t < 4; ++t) pq[t] = nq[t];
                 }
-                if (pub) {
+                if (lane == k + 1) {
 #pragma unroll
                     for (int j = 1; j < N - 1; ++j) {
                         if ((j & 3) == 1 && j >= lim) break;
@@ -774,9 +781,9 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 __syncwarp();
             }
             bad = __any_sync(FULL, bad && rv) || (p.force_pivot != 0);
-            if (!rv) lacc = 0.f;
             if (bad) {                              // rare: redo with the partially pivoted LU on the staged copy
                 lacc = pivoted_lu_smem<N>(reinterpret_cast<float*>(sJ), lane);     // all 32 lanes own scalar rows here
+                lacc_per_lane = true;
                 if (lane == 0 && p.fallback_counter) atomicAdd(p.fallback_counter, 1ull);
             }
         }
@@ -840,7 +847,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
             // row offers its new register 0; one REDUX picks the next pivot row, which publishes 1/pivot (the
             // reciprocal chain overlaps the remaining updates) and then its row.  Finished rows compute garbage.
             bool done = !rv, singular = false;
-            double mypn = 1.0, pncand = 1.0;
+            double mypn = 1.0;
             constexpr int LP = N + 8;
             double2* const dline0 = reinterpret_cast<double2*>(sm + L_::o_H);    // [2][LP]
             auto offer = [&](const double2 e) -> unsigned {
@@ -848,17 +855,21 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x1Fu) | (unsigned)lane);
                 return __reduce_max_sync(FULL, key);
             };
-            auto publish_inv = [&](const double2 e, double2* slot) {
-                const double pn = fma(e.x, e.x, e.y * e.y);
-                double ip = (double)rcp_approx((float)pn);                 // 1/pn: FP32 seed + 2 Newton steps
-                ip = ip * (2.0 - pn * ip);
-                ip = ip * (2.0 - pn * ip);
-                *slot = make_double2(e.x * ip, -e.y * ip);
-                pncand = pn;
+            // 1/pivot, computed by EVERY lane from the shuffled pivot (no divergent branch, no shared-memory round trip):
+            // FP32 seed of 1/|e|^2 from the FP32-rounded entry + one float64 Newton step (2^-23 squared)
+            double pn = 1.0;
+            auto pivot_inv = [&](const double2 e) -> double2 {
+                pn = fma(e.x, e.x, e.y * e.y);
+                const float ex = (float)e.x, ey = (float)e.y;
+                const double r0 = (double)rcp_approx(fmaf(ex, ex, ey * ey));
+                const double ip = r0 * (2.0 - pn * r0);
+                return make_double2(e.x * ip, -e.y * ip);
             };
             unsigned wk = offer(Dr[0]);
-            if (!done && lane == (int)(wk & 31u) && (wk >> 5) != 0u) {
-                publish_inv(Dr[0], dline0 + N);
+            double2 iv = pivot_inv(shfl2dw(Dr[0], (int)(wk & 31u)));
+            bool win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
+            if (win) {
+                mypn = pn;
 #pragma unroll
                 for (int j = 1; j < N; ++j) dline0[j] = Dr[j];
             }
@@ -869,13 +880,11 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 double2* nxt = dline0 + ((k + 1) & 1) * LP;
                 const int lim = N - 1 - k;
                 singular |= (wk >> 5) == 0u;
-                if (!done && lane == (int)(wk & 31u)) { done = true; mypn = pncand; }
+                done |= win;
                 if (lim == 0) break;
-                const double2 iv = cur[N];
                 const double2 c = Dr[0];
                 const double lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
                 const double ly = -(c.x * iv.y + c.y * iv.x);
-                bool win = false;
                 double2 pq[4] = {cur[1], cur[2], cur[3], cur[4]};
 #pragma unroll
                 for (int j0 = 1; j0 < N; j0 += 4) {
@@ -899,8 +908,9 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                             Dr[j - 1] = v;
                             if (j == 1) {
                                 wk = offer(v);
+                                iv = pivot_inv(shfl2dw(v, (int)(wk & 31u)));
                                 win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
-                                if (win) publish_inv(v, nxt + N);
+                                if (win) mypn = pn;
                             }
                         }
                     }
@@ -920,7 +930,8 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
             aD = warp_sum_f64(aD);
             if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
         }
-        const double aJ = warp_sum_f64((double)lacc * 0.693147180559945309417);
+        const double aJ = lacc_per_lane ? warp_sum_f64((double)lacc * 0.693147180559945309417)
+                                        : (double)lacc * 0.693147180559945309417;
 
         // ---------------- Metropolis accept / reject (MCMC.py:28-33), warp-uniform ------------------------------
         const double ldD = aD - nlogL;
