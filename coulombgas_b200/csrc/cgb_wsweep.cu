@@ -1026,6 +1026,10 @@ int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
     if (!wsweep_supported(p.n)) return CGB_E_UNSUPPORTED;
     if ((unsigned long long)p.B * (unsigned long long)(p.mc_steps + 2) >= (1ull << 31)) return CGB_E_UNSUPPORTED;
     if (p.wconst != wconst_staging) return CGB_E_BADARG;
+    // the constant bank is per device: make sure it is the stream's device that gets refreshed and launched on
+    int cur_dev = 0, st_dev = -1;
+    cudaGetDevice(&cur_dev);
+    if (st != nullptr && cudaStreamGetDevice(st, &st_dev) == cudaSuccess && st_dev != cur_dev) return CGB_E_BADARG;
     prep_wconst_kernel<<<1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

@@ -248,3 +248,61 @@ def test_empty_and_single_walker(cg, cases):
     assert abs(one[0] - c["ref_logp"][0]) < RTOL * abs(c["ref_logp"][0])
     with pytest.raises(TypeError):
         cg.mcmc(lambda x: x, c["x"][:1], 0, 3, 0.1)
+
+
+# ------------------------------------------------------------------ warp-per-walker kernel specifics
+@pytest.mark.parametrize("tag", ["n13_rs10", "n29_rs1"])
+def test_cta_kernel_still_matches_golden(cg, cases, tag, monkeypatch):
+    """n = 13 / 29 are dispatched to the warp-per-walker kernel; the CTA-per-walker kernel (used for every other n)
+    must keep reproducing the reference's own run on the same shapes (CGB_SWEEP_KERNEL=cta forces it)."""
+    monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
+    c = cases(tag)
+    nb = c["mc_x0"].shape[0]
+    logp = cg.make_logp(c["ktable"], c["L"])
+    lp = logp(c["x"][:nb], c["params"], c["state_idx"][:nb])
+    assert (np.abs(lp - c["ref_logp"][:nb]) < RTOL * np.abs(c["ref_logp"][:nb])).all()
+    x, acc = cg.mcmc(logp.bind(c["params"], c["state_idx"][:nb]), c["mc_x0"].copy(),
+                     cg.ExplicitNoise(c["mc_noise"], c["mc_uniforms"]), c["mc_steps"], c["mc_stddev"])
+    assert abs(acc - c["ref_mc_accept_rate"]) < 1e-12
+    assert np.abs(x - c["ref_mc_x"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("B", [1, 3, 37, 300, 2500])
+def test_ready_queue_any_batch_size(cg, cases, B, monkeypatch):
+    """The proposal-granular ready queue of the warp kernel must give, for every batch size (fewer walkers than
+    warps, non-multiples of anything, more walkers than resident warps), the same chains as the CTA kernel, which
+    runs each walker start to finish in one block: both draw from the same Philox streams keyed by (walker, step)."""
+    c = cases("n29_rs1")
+    S = 6
+    reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+    rng = np.random.default_rng(5)
+    x0 = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2))
+    si = np.tile(c["state_idx"], (reps, 1))[:B]
+    logp = cg.make_logp(c["ktable"], c["L"])
+    xw, accw, trw = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, return_trace=True)
+    monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
+    xc, accc, trc = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, return_trace=True)
+    assert (np.abs(trw["logp_prop"][0] - trc["logp_prop"][0]) < RTOL * np.abs(trc["logp_prop"][0])).all()
+    same = (trw["accept"] == trc["accept"]).all(axis=0)
+    assert (~same).sum() <= max(1, B // 500), "chains diverged on %d of %d walkers" % ((~same).sum(), B)
+    assert np.abs(xw[same] - xc[same]).max() < 1e-12
+    assert np.array_equal(trw["naccept"][same], trc["naccept"][same])
+    assert np.abs(trw["logp"][same] - trc["logp"][same]).max() < RTOL * np.abs(trc["logp"]).max()
+
+
+def test_large_wavevectors_use_the_staged_slater_path(cg, oracle):
+    """|m| beyond the per-particle power tables (13 at n = 13): the Slater rows are computed entry by entry and
+    staged through shared memory; compare with the oracle."""
+    from oracle import flow as oflow, tables
+    rng = np.random.default_rng(21)
+    kt, _ = tables.ktable(2, 260, (0.25, 0.25))           # descending energy: rows 0.. have |m| up to 16
+    n = 13
+    L = float(np.sqrt(np.pi * n))
+    p = oflow.init_params(2, 16, 16, 2, seed=4, stddev=0.1)
+    x = rng.uniform(0, L, (6, n, 2))
+    si = np.stack([np.sort(np.concatenate([rng.choice(40, 5, replace=False), 40 + rng.choice(kt.shape[0] - 40, n - 5, replace=False)]))
+                   for _ in range(6)]).astype(np.int32)
+    assert np.abs(np.rint(kt[si] - 0.25)).max() > 13
+    lp = cg.make_logp(kt, L)(x, p, si)
+    ref = oracle["logpsi"].logp_batch(x, p, si, kt, L)
+    assert np.abs(lp - ref).max() < RTOL * np.abs(ref).max(), np.abs(lp - ref).max()
