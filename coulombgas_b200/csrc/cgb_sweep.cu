@@ -10,9 +10,11 @@
 // In the two O(n^2) pair passes lane q of row i handles partners j = q, q+4, ...; row sums are 2-stage
 // shuffle butterflies inside the 4-lane group, so no cross-warp reduction buffers are needed.
 // Weights live in shared memory (broadcast LDS.128); per-row contractions Q_i, R_i in registers.
-// LU: one thread per matrix row, rows in shared memory (odd pitch -> conflict-free), pivot search by a
-// single REDUX (integer max of |a| bits with the row id in the low bits) + one named barrier per step;
-// the real 2n x 2n (Jacobian) and complex n x n (Slater) factorisations run concurrently on disjoint warps.
+// LU: both factorisations (real 2n x 2n Jacobian as unpivoted 2x2-block LU, complex n x n Slater matrix with
+// partial pivoting) are register-resident and use all threads: thread (row, q) keeps columns q, q+4, ... of its
+// row, the active column is broadcast inside the quad by shuffle, the pivot line travels through a
+// double-buffered shared-memory line and there is ONE block barrier per elimination step (pivot search: one
+// REDUX per warp on |a| bits with the row id in the low bits; every warp publishes its candidate row).
 #include "cgb_common.cuh"
 #include "cgb_internal.h"
 
@@ -56,23 +58,22 @@ struct Lay {
     static constexpr int ptab_bytes = 16 * N8 + 64 * N8 + 144 * N8;
     static constexpr int o_H = o_s0 + 64 * N8;        // float[N8*36] H_k   (aliases double[N8*18] h_i: dead before H is written)
     static constexpr int o_red = o_H + 144 * N8;      // unsigned[2*8] J pivots, unsigned[2*8] D pivots, int[4] flags
-    static constexpr int o_J = o_red + 160;           // float4[n*pitchB] Jacobian as 2x2 blocks; then max(R|T float[2*N8*36], D double2[n*pitchD])
+    static constexpr int o_J = o_red + 160;           // float4[n*pitchB] Jacobian as 2x2 blocks; then R|T float[2*N8*36] (later the LU pivot lines)
     static_assert(o_J % 16 == 0, "alignment");
 };
 __host__ __device__ inline int pitch_B(int n) { return n | 1; }   // float4 blocks per block-row, odd: conflict-free LDS.128
-__host__ __device__ inline int pitch_D(int n) { return n | 1; }                          // odd: conflict-free 16-byte rows
 
 size_t sweep_smem_bytes(int n) {
     const int n8 = 8 * sweep_num_warps(n);
     const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160);
     const size_t jb = sizeof(float4) * n * pitch_B(n);
-    const size_t rt = sizeof(float) * n8 * 36 * 2, dd = sizeof(double2) * n * pitch_D(n);
-    return fixed + jb + (rt > dd ? rt : dd);
+    const size_t rt = sizeof(float) * n8 * 36 * 2;      // R|T rows; afterwards the LU pivot lines (<= rt for NW <= 8)
+    return fixed + jb + rt;
 }
 
 struct Smem {
     float* wts; double* xs; double* xp; float4* pos; double2* us; int2* kint; double2* ptab; double2* dz; float* sig0;
-    double* hbuf; double* hbar; float* Rbuf; float* Tbuf; float* Hbuf; float4* J; double2* D;
+    double* hbuf; double* hbar; float* Rbuf; float* Tbuf; float* Hbuf; float4* J;
     unsigned* redJ; unsigned* redD; double* lsum; int* flag;
 };
 
@@ -142,7 +143,7 @@ sweep_kernel(const SweepParams p) {
     constexpr int n8 = 8 * NW;
     using L_ = Lay<n8>;
     static_assert(L_::o_J == 16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160, "host size formula");
-    const int N2 = 2 * n, pB = pitch_B(n), pD = pitch_D(n);
+    const int N2 = 2 * n, pB = pitch_B(n);
     Smem s;
     s.xs = (double*)(smem_raw + L_::o_xs); s.xp = (double*)(smem_raw + L_::o_xp); s.lsum = (double*)(smem_raw + L_::o_ls);
     s.hbar = (double*)(smem_raw + L_::o_hb); s.us = (double2*)(smem_raw + L_::o_us); s.dz = (double2*)(smem_raw + L_::o_dz);
@@ -150,12 +151,8 @@ sweep_kernel(const SweepParams p) {
     s.sig0 = (float*)(smem_raw + L_::o_s0); s.Hbuf = (float*)(smem_raw + L_::o_H); s.hbuf = (double*)(smem_raw + L_::o_H);
     s.redJ = (unsigned*)(smem_raw + L_::o_red); s.redD = s.redJ + 16; s.flag = (int*)(s.redJ + 32);
     s.J = (float4*)(smem_raw + L_::o_J);     // block (i,k) = (J[2i][2k], J[2i][2k+1], J[2i+1][2k], J[2i+1][2k+1])
-    s.Rbuf = (float*)(s.J + n * pB); s.Tbuf = s.Rbuf + n8 * 36; s.D = (double2*)s.Rbuf;
-    // LU warps: Jacobian on [0,nJw), Slater on [nJw, nJw+nDw); both counts follow from NW = ceil(n/8)
-    constexpr int nJw = (NW + 1) / 2, nDw = NW >= 5 ? 2 : 1;
-    constexpr int nBw = nDw;          // warps of the block-LU fast path (one thread per 2x2 block-row)
-    constexpr int nSw = NW - nJw;     // warps that build the Slater matrix; the first nDw of them factorise it
-    static_assert(nJw + nDw <= NW, "warp roles");
+    s.Rbuf = (float*)(s.J + n * pB); s.Tbuf = s.Rbuf + n8 * 36;
+    constexpr int nJw = (NW + 1) / 2;  // warps of the pivoted fallback LU of the Jacobian (one thread per scalar row)
     const float invn = 1.f / (float)n;
     const double invL = 1.0 / p.L;
     const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
@@ -547,47 +544,100 @@ sweep_kernel(const SweepParams p) {
                 __syncthreads();
             }
 
-            // ---------------- LU phase: real 2n x 2n FP32 Jacobian || complex n x n FP64 Slater matrix ---------
-            // Jacobian: J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU, one
-            // thread per block-row (2 rows), blocks in shared memory: log|det J| = sum_k log|det P_kk|.  Half the
-            // sequential depth of a scalar LU, no pivot search, no cross-warp exchange.  Multipliers and pivot
-            // determinants are monitored; if they leave the safe range the whole evaluation is redone with the
-            // partially pivoted scalar LU below (use_pivot), so arbitrary parameters stay correct.
-            if (!use_pivot && warp < nBw) {
-                const int bi = tid;
-                const bool act = bi < n;
-                float4* brow = s.J + (act ? bi : 0) * pB;
+            // ---------------- LU phase: real 2n x 2n FP32 Jacobian, then complex n x n FP64 Slater matrix ---------
+            // Both factorisations are REGISTER-RESIDENT and use every thread of the CTA: thread (row, q) keeps the
+            // blocks / entries j = q, q+4, ... of its row (the layout the pair passes already produce), MB = 2 NW
+            // per thread.  Step k = 4 base + s: the active column is register 0 of quad lane s (broadcast by shuffle);
+            // every fourth step the update writes slot m into slot m-1, so register indices stay compile-time in a
+            // rolled loop.  Only the pivot line travels through shared memory (double-buffered), one block barrier
+            // per elimination step; warps whose rows are all finished skip the arithmetic and only keep the barrier.
+            // Jacobian: J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU
+            // (log|det J| = sum_k log|det P_kk|); multipliers and pivot determinants are monitored and an evaluation
+            // that leaves the safe range is redone with the partially pivoted scalar LU below (use_pivot).
+            constexpr int MB = 2 * NW, LP = 4 * MB + 4;
+            const int qbase = lane & ~3;
+            if (warp == NW - 1) {        // mean backflow displacement (a pure phase of det D; keeps the phases small)
+                double mx = 0.0, my = 0.0;
+                for (int t = lane; t < n; t += 32) { const double2 v = s.dz[t]; mx += v.x; my += v.y; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { mx += __shfl_xor_sync(0xffffffffu, mx, o); my += __shfl_xor_sync(0xffffffffu, my, o); }
+                if (lane == 0) { s.lsum[12] = mx / (double)n; s.lsum[13] = my / (double)n; }
+            }
+            if (!use_pivot) {
+                float4* const jline = reinterpret_cast<float4*>(s.Rbuf);        // [2][LP]  (R|T rows are dead)
+                float4 Jr[MB];
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                    const int j = 4 * m + q;
+                    Jr[m] = (rv && j < n) ? s.J[row * pB + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (row == 0) {
+#pragma unroll
+                    for (int m = 0; m < MB; ++m) jline[4 * m + q] = Jr[m];
+                }
                 float lacc = 0.f;
                 bool bad = false;
-                for (int k = 0; k < n; ++k) {
-                    if (nBw > 1) named_bar_sync(1, nBw * 32); else __syncwarp();
-                    const float4* prow = s.J + k * pB;
-                    const float4 pk = prow[k];                              // pivot block (broadcast)
-                    const float det = pk.x * pk.w - pk.y * pk.z;
-                    const float idet = rcp_approx(det);
-                    lacc += lg2_approx(fabsf(det));                          // identical in every lane
-                    bad |= !(fabsf(det) > 0.05f);                            // also catches NaN
-                    if (act && bi > k) {
-                        const float4 a = brow[k];
-                        // -L = -A_ik P_kk^{-1},  P^{-1} = [[w,-y],[-z,x]] / det
-                        const float l00 = (a.y * pk.z - a.x * pk.w) * idet, l01 = (a.x * pk.y - a.y * pk.x) * idet;
-                        const float l10 = (a.w * pk.z - a.z * pk.w) * idet, l11 = (a.z * pk.y - a.w * pk.x) * idet;
-                        bad |= (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
-#pragma unroll 4
-                        for (int j = k + 1; j < n; ++j) {
-                            const float4 qv = prow[j];
-                            float4 v = brow[j];
-                            v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
-                            v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
-                            v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
-                            v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
-                            brow[j] = v;
+                __syncthreads();
+                for (int base = 0; 4 * base < n; ++base) {
+#pragma unroll
+                    for (int sst = 0; sst < 4; ++sst) {
+                        const int k = 4 * base + sst;
+                        if (k >= n) break;
+                        const float4* cur = jline + (k & 1) * LP;
+                        float4* nxt = jline + ((k + 1) & 1) * LP;
+                        const float4 pk = cur[k];                                // pivot block (broadcast)
+                        const float det = pk.x * pk.w - pk.y * pk.z;
+                        const float idet = rcp_approx(det);
+                        lacc += lg2_approx(fabsf(det));                          // identical in every thread
+                        bad |= !(fabsf(det) > 0.05f);                            // also catches NaN
+                        if (k == n - 1) break;
+                        if (8 * warp + 7 > k) {                                  // this warp still has live rows
+                            float4 a;
+                            a.x = __shfl_sync(0xffffffffu, Jr[0].x, qbase + sst); a.y = __shfl_sync(0xffffffffu, Jr[0].y, qbase + sst);
+                            a.z = __shfl_sync(0xffffffffu, Jr[0].z, qbase + sst); a.w = __shfl_sync(0xffffffffu, Jr[0].w, qbase + sst);
+                            // -L = -A_ik P_kk^{-1},  P^{-1} = [[w,-y],[-z,x]] / det
+                            const float l00 = (a.y * pk.z - a.x * pk.w) * idet, l01 = (a.x * pk.y - a.y * pk.x) * idet;
+                            const float l10 = (a.w * pk.z - a.z * pk.w) * idet, l11 = (a.z * pk.y - a.w * pk.x) * idet;
+                            bad |= (rv && row > k) && (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
+#pragma unroll
+                            for (int m = 0; m < MB; ++m) {
+                                if (4 * (base + m) >= n) break;                  // uniform: the live tail shrinks with base
+                                const int j = 4 * (base + m) + q;
+                                if (sst == 3) {
+                                    if (m >= 1) {
+                                        const float4 qv = cur[j];
+                                        float4 v = Jr[m];
+                                        v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
+                                        v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
+                                        v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
+                                        v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
+                                        Jr[m - 1] = v;                           // shift: column 4(base+1)+q moves to slot 0
+                                    }
+                                } else if (m > 0 || q > sst) {
+                                    const float4 qv = cur[j];
+                                    float4 v = Jr[m];
+                                    v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
+                                    v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
+                                    v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
+                                    v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
+                                    Jr[m] = v;
+                                }
+                            }
+                            if (row == k + 1) {                                  // publish the next pivot line
+                                const int nb = (k + 1) >> 2;
+#pragma unroll
+                                for (int m = 0; m < MB; ++m) {
+                                    if (4 * (nb + m) >= n) break;
+                                    nxt[4 * (nb + m) + q] = Jr[m];
+                                }
+                            }
                         }
+                        __syncthreads();
                     }
                 }
                 if (__any_sync(0xffffffffu, bad) && lane == 0) s.flag[2] = 1;
-                if (tid == 0) s.lsum[0] = (double)lacc * 0.693147180559945309417;
-            } else if (use_pivot && warp < nJw) {
+                if (tid == 0) s.lsum[15] = (double)lacc * 0.693147180559945309417;
+            } else if (warp < nJw) {
                 // ---- fallback: scalar LU with partial pivoting on the blocked storage, one thread per row.
                 // |a| bits with the row id in the low 7 bits -> one REDUX per warp; per-warp maxima exchanged
                 // through a double-buffered slot, one named barrier per elimination step.
@@ -621,21 +671,18 @@ sweep_kernel(const SweepParams p) {
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (lane == 0) s.lsum[8 + warp] = acc * 0.693147180559945309417;
             }
-            if (warp >= NW - nSw) {
-                // ---- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + (dz - mean dz)/L
-                // (src/slater.py:14-17; the twist and the common displacement are pure row/column phases
-                // and drop out of |det|).  All warps >= nJw build entries; the first nDw of them factorise.
-                constexpr int nb = nSw * 32;
-                const int t2 = tid - nJw * 32;
+            __syncthreads();
+            if (use_pivot || s.flag[2] == 0) {
+                // ---- Slater matrix in float64, built straight into registers: D_rj = exp(2 pi i m_j . w_r),
+                // w = u + (dz - mean dz)/L  (src/slater.py:14-17; the twist and the common displacement are pure
+                // row/column phases and drop out of |det|).
                 const int mmax = s.flag[1];                      // max |m| over this walker's occupied orbitals
-                if (mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes) {
+                const bool tab = mmax > 0 && (size_t)n * 2 * mmax * sizeof(double2) <= (size_t)L_::ptab_bytes;
+                const double mdx = s.lsum[12], mdy = s.lsum[13];
+                if (tab) {
                     // power tables  X_r^m = e^{2 pi i m w_rx},  Y_r^m,  m = 1..mmax  (one sincospi per coordinate)
-                    for (int c = t2; c < 2 * n; c += nb) {
-                        const int rr = c >> 1, comp = c & 1;
-                        double mean = 0.0;
-                        for (int t = 0; t < n; ++t) mean += reinterpret_cast<const double*>(s.dz)[2 * t + comp];
-                        mean /= (double)n;
-                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[c] - mean, invL,
+                    for (int c = tid; c < 2 * n; c += NW * 32) {
+                        const double wv = fma(reinterpret_cast<const double*>(s.dz)[c] - ((c & 1) ? mdy : mdx), invL,
                                               reinterpret_cast<const double*>(s.us)[c]);
                         double sn, cs;
                         sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
@@ -647,109 +694,113 @@ sweep_kernel(const SweepParams p) {
                             tb[m] = pw;
                         }
                     }
-                    if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
-                    for (int j = t2 >> 5; j < n; j += nb / 32) {
-                        const int rr = t2 & 31;
-                        const int2 mk = s.kint[j];
+                    __syncthreads();
+                }
+                double2 Dr[MB];
+                {
+                    const double2 uu = s.us[i], dd = s.dz[i];
+                    const double wx = fma(dd.x - mdx, invL, uu.x), wy = fma(dd.y - mdy, invL, uu.y);
 #pragma unroll
-                        for (int half = 0; half < (NW > 4 ? 2 : 1); ++half) {
-                            const int r2 = rr + 32 * half;
-                            if (r2 < n) {
+                    for (int m = 0; m < MB; ++m) {
+                        const int j = 4 * m + q;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (rv && j < n) {
+                            const int2 mk = s.kint[j];
+                            if (tab) {
                                 const int ax = abs(mk.x), ay = abs(mk.y);
                                 double2 X = make_double2(1.0, 0.0), Y = make_double2(1.0, 0.0);
-                                if (ax) { X = s.ptab[(size_t)(2 * r2) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
-                                if (ay) { Y = s.ptab[(size_t)(2 * r2 + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
-                                s.D[r2 * pD + j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                                if (ax) { X = s.ptab[(size_t)(2 * row) * mmax + ax - 1]; if (mk.x < 0) X.y = -X.y; }
+                                if (ay) { Y = s.ptab[(size_t)(2 * row + 1) * mmax + ay - 1]; if (mk.y < 0) Y.y = -Y.y; }
+                                v = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                            } else {
+                                double ph = fma((double)mk.x, wx, (double)mk.y * wy);
+                                ph -= rint(ph);
+                                double sn, cs;
+                                sincospi(2.0 * ph, &sn, &cs);
+                                v = make_double2(cs, sn);
                             }
                         }
-                    }
-                } else {
-                    double mx = 0.0, my = 0.0;
-                    for (int t = 0; t < n; ++t) { const double2 v = s.dz[t]; mx += v.x; my += v.y; }
-                    mx /= (double)n; my /= (double)n;
-                    for (int idx = t2; idx < n * n; idx += nb) {
-                        const int rr = idx / n, j = idx - rr * n;
-                        const double2 uu = s.us[rr], dd = s.dz[rr];
-                        const double wx = fma(dd.x - mx, invL, uu.x), wy = fma(dd.y - my, invL, uu.y);
-                        const int2 mk = s.kint[j];
-                        double ph = fma((double)mk.x, wx, (double)mk.y * wy);
-                        ph -= rint(ph);
-                        double sn, cs;
-                        sincospi(2.0 * ph, &sn, &cs);
-                        s.D[rr * pD + j] = make_double2(cs, sn);
+                        Dr[m] = v;
                     }
                 }
-                if (nSw > 1) named_bar_sync(3, nb); else __syncwarp();
-                if (warp < nJw + nDw) {
-                    const int dw = warp - nJw;
-                    const int r = t2;
-                    double2* base = s.D + (r < n ? r : 0) * pD;
-                    bool done = !(r < n);
-                    double mylog = 0.0;
-                    double2 cur = done ? make_double2(0.0, 0.0) : base[0];
-                    unsigned wnext;
-                    {
-                        const float mag = (float)(fabs(cur.x) + fabs(cur.y));
-                        const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
-                        wnext = __reduce_max_sync(0xffffffffu, key);
-                        if (nDw > 1 && lane == 0) s.redD[dw] = wnext;
-                    }
-                    for (int k = 0; k < n; ++k) {
-                        unsigned gmax = wnext;
-                        if (nDw > 1) {
-                            named_bar_sync(2, nDw * 32);
+                // ---- Slater LU: partially pivoted, implicit row exchange.  After its update every unfinished row
+                // offers its entry of the next column; one REDUX per warp picks the warp's candidate row, which is
+                // published right away into the warp's own line slot together with its key, so ONE block barrier per
+                // step suffices: after it every thread reads the NW keys, takes the best and reads that warp's slot.
+                double2* const dslots = reinterpret_cast<double2*>(s.Rbuf);       // [2][NW][LP]
+                bool done = !rv, singular = false;
+                double mypn = 1.0;
+                auto offer_publish = [&](int kn) {        // candidates for pivot column kn (held in slot 0 of quad lane kn&3)
+                    const float mag = (float)(fabs(Dr[0].x) + fabs(Dr[0].y));
+                    const unsigned key = (done || q != (kn & 3)) ? 0u : ((__float_as_uint(mag) & ~0x3Fu) | (unsigned)row);
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0) s.redD[(kn & 1) * 8 + warp] = wmax;
+                    if ((wmax >> 6) != 0u && row == (int)(wmax & 0x3Fu)) {
+                        double2* slot = dslots + ((kn & 1) * NW + warp) * LP;
+                        const int nb = kn >> 2;
 #pragma unroll
-                            for (int w = 0; w < nDw; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
-                        } else {
-                            __syncwarp();
+                        for (int m = 0; m < MB; ++m) {
+                            if (4 * (nb + m) >= n) break;
+                            slot[4 * (nb + m) + q] = Dr[m];
                         }
-                        const int pr = (int)(gmax & 0x7Fu);
-                        const double2* prow = s.D + pr * pD;
-                        const double2 piv = prow[k];
+                    }
+                };
+                offer_publish(0);
+                __syncthreads();
+                for (int base = 0; 4 * base < n; ++base) {
+#pragma unroll
+                    for (int sst = 0; sst < 4; ++sst) {
+                        const int k = 4 * base + sst;
+                        if (k >= n) break;
+                        unsigned gmax = s.redD[(k & 1) * 8];
+#pragma unroll
+                        for (int w = 1; w < NW; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                        singular |= (gmax >> 6) == 0u;
+                        const int pr = (int)(gmax & 0x3Fu);
+                        const double2* cur = dslots + ((k & 1) * NW + (pr >> 3)) * LP;
+                        const double2 piv = cur[k];
                         const double pn = fma(piv.x, piv.x, piv.y * piv.y);
-                        if (r == pr) {
-                            done = true;
-                            mylog = pn;                            // log taken once, after the loop
-                        }
-                        const bool upd = !done;
-                        double lx = 0.0, ly = 0.0;
-                        if (upd) {
-                            double ip = (double)rcp_approx((float)pn);   // 1/pn: FP32 seed + 2 Newton steps
+                        if (tid == k) mypn = pn;                               // log taken once, after the loop
+                        if (row == pr) done = true;
+                        if (k == n - 1) break;
+                        if (!__all_sync(0xffffffffu, done)) {
+                            double ip = (double)rcp_approx((float)pn);          // 1/pn: FP32 seed + 2 Newton steps
                             ip = ip * (2.0 - pn * ip);
-                            ip = ip * (2.0 - pn * ip);               // l = -cur / piv
-                            lx = -(cur.x * piv.x + cur.y * piv.y) * ip;
-                            ly = -(cur.y * piv.x - cur.x * piv.y) * ip;
-                            if (k + 1 < n) {
-                                const double2 pv = prow[k + 1];
-                                double2 v = base[k + 1];
-                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
-                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                                base[k + 1] = v;
-                                cur = v;
-                            }
-                        }
-                        {
-                            const float mag = (float)(fabs(cur.x) + fabs(cur.y));
-                            const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x7Fu) | (unsigned)r);
-                            wnext = __reduce_max_sync(0xffffffffu, key);
-                            if (nDw > 1 && lane == 0) s.redD[((k + 1) & 1) * 8 + dw] = wnext;
-                        }
-                        if (upd) {
-#pragma unroll 2
-                            for (int j = k + 2; j < n; ++j) {
-                                const double2 pv = prow[j];
-                                double2 v = base[j];
-                                v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
-                                v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
-                                base[j] = v;
-                            }
-                        }
-                    }
-                    double acc = (r < n) ? 0.5 * log(mylog) : 0.0;
+                            ip = ip * (2.0 - pn * ip);
+                            const double ivx = piv.x * ip, ivy = -piv.y * ip;   // 1 / pivot
+                            const double cx = __shfl_sync(0xffffffffu, Dr[0].x, qbase + sst);
+                            const double cy = __shfl_sync(0xffffffffu, Dr[0].y, qbase + sst);
+                            const double lx = -(cx * ivx - cy * ivy), ly = -(cx * ivy + cy * ivx);   // l = -c / pivot
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (lane == 0) s.lsum[warp] = acc;
+                            for (int m = 0; m < MB; ++m) {
+                                if (4 * (base + m) >= n) break;
+                                const int j = 4 * (base + m) + q;
+                                if (sst == 3) {
+                                    if (m >= 1) {
+                                        const double2 pv = cur[j];
+                                        double2 v = Dr[m];
+                                        v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                        v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                        Dr[m - 1] = v;
+                                    }
+                                } else if (m > 0 || q > sst) {
+                                    const double2 pv = cur[j];
+                                    double2 v = Dr[m];
+                                    v.x = fma(lx, pv.x, fma(-ly, pv.y, v.x));
+                                    v.y = fma(lx, pv.y, fma(ly, pv.x, v.y));
+                                    Dr[m] = v;
+                                }
+                            }
+                        }
+                        offer_publish(k + 1);
+                        __syncthreads();
+                    }
                 }
+                double acc = (tid < n) ? 0.5 * log(mypn) : 0.0;
+                if (singular) acc = -INFINITY;            // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s.lsum[warp] = acc;
             }
             __syncthreads();
             if (use_pivot || s.flag[2] == 0) break;
@@ -760,8 +811,8 @@ sweep_kernel(const SweepParams p) {
             // ---------------- Metropolis accept / reject (MCMC.py:28-33) ------------------------------
             if (tid == 0) {
                 double ldJ = 0.0, ldD = 0.0;
-                if (use_pivot) { for (int w = 0; w < nJw; ++w) ldJ += s.lsum[8 + w]; } else { ldJ = s.lsum[0]; }
-                for (int w = nJw; w < nJw + nDw; ++w) ldD += s.lsum[w];
+                if (use_pivot) { for (int w = 0; w < nJw; ++w) ldJ += s.lsum[8 + w]; } else { ldJ = s.lsum[15]; }
+                for (int w = 0; w < NW; ++w) ldD += s.lsum[w];
                 ldD -= (double)n * log(p.L);                     // D carries L^{-dim/2} per entry (slater.py:17)
                 const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179
                 int acc = 1;

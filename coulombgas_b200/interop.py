@@ -1,0 +1,249 @@
+"""Interop with the reference's on-disk formats and host-side setup tables (SURVEY §8 rows a9/a10 and f/N1):
+
+* single-particle orbital table  sp_orbitals / twist_sort / sp_indices_twist   (src/orbitals.py:22-55, main.py:79-90)
+* run directory name and checkpoint file names                                  (main.py:194-206, src/checkpoint.py:4-8)
+* checkpoint reader / writer that needs neither jax, haiku nor optax            (src/checkpoint.py:10-17, main.py:376-384)
+* walker / key sharding of a checkpoint over ranks                              (main.py:217-223, 231-238)
+* `data.txt` line writer and reader                                             (main.py:355-374)
+
+Pure NumPy + pickle: no device code here; everything the kernels consume from a reference run passes through
+this module, so a run written by the reference's main.py can be replayed through libcgb200.so (tools/replay_checkpoint.py).
+"""
+import io
+import os
+import pickle
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------------
+# host-side setup tables
+# ----------------------------------------------------------------------------------------------------
+
+
+def box_length(n, dim=2):
+    """main.py:63-67: box length at unit rs (the kernels work in these units; rs only scales the energy)."""
+    if dim == 2:
+        return float(np.sqrt(np.pi * n))
+    if dim == 3:
+        return float((4.0 / 3.0 * np.pi * n) ** (1.0 / 3.0))
+    raise ValueError("dim must be 2 or 3")
+
+
+def _lattice(dim, nmax):
+    """All integer vectors of [-nmax, nmax]^dim in numpy.meshgrid('xy').flatten order — the enumeration order is part
+    of the contract: ties in energy are broken by numpy's default argsort acting on THIS order (orbitals.py:36-42)."""
+    axis = np.arange(-nmax, nmax + 1)
+    mesh = np.meshgrid(*([axis] * dim))
+    return np.stack([m.reshape(-1) for m in mesh], axis=1)
+
+
+def sp_orbitals(dim, Emax=60):
+    """src/orbitals.py:22-44 -> (indices (M, dim) int, Es (M,) int), ascending |m|^2 <= Emax."""
+    lat = _lattice(dim, int(np.floor(np.sqrt(Emax))))
+    e = np.sum(lat * lat, axis=1)
+    sel = e <= Emax
+    lat, e = lat[sel], e[sel]
+    perm = e.argsort()          # numpy default kind, as the reference: tie order must be reproduced, not improved
+    return lat[perm], e[perm]
+
+
+def twist_sort(indices, twist):
+    """src/orbitals.py:46-55 -> (indices + twist re-sorted by twisted energy, twisted energies)."""
+    kt = np.asarray(indices) + np.asarray(twist, dtype=np.float64)
+    e = np.sum(kt * kt, axis=1)
+    perm = e.argsort()
+    return kt[perm], e[perm]
+
+
+def sp_indices_twist(dim, Emax, twist):
+    """main.py:79-90: the (M, dim) float64 k-table the kernels take as `ktable`, DESCENDING twisted energy
+    (row M-1 is the lowest orbital; the ground state occupies rows M-n..M-1, main.py:101)."""
+    idx, _ = sp_orbitals(dim, Emax)
+    kt, e = twist_sort(idx, twist)
+    return np.ascontiguousarray(kt[::-1], dtype=np.float64), np.ascontiguousarray(e[::-1], dtype=np.float64)
+
+
+def ground_state_indices(M, n):
+    """main.py:101 (`jnp.arange(num_states - n, num_states)`): the n lowest twisted orbitals."""
+    return np.arange(M - n, M, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------------------------------
+# file names
+# ----------------------------------------------------------------------------------------------------
+
+
+def run_dirname(folder, *, n, dim, rs, Theta, Emax, twist, nlayers, modelsize, nheads, nhidden, depth, spsize, tpsize,
+                Gmax, kappa, mc_therm, mc_steps, mc_stddev, batch, num_devices, acc_steps, hutchinson=False,
+                sr=True, damping=1e-3, max_norm=1e-3, lr=1e-3):
+    """The run directory main.py:194-206 derives from its flags (every hyper-parameter is encoded in the name)."""
+    s = folder + "n_%d_dim_%d_rs_%.1f_Theta_%.2f" % (n, dim, rs, Theta)
+    s += "_Emax_%d" % Emax
+    s += ("_twist" + "_%.3f" * dim) % tuple(twist)
+    s += "_nlayers_%d_modelsize_%d_nheads_%d_nhidden_%d" % (nlayers, modelsize, nheads, nhidden)
+    s += "_depth_%d_spsize_%d_tpsize_%d" % (depth, spsize, tpsize)
+    s += "_Gmax_%d_kappa_%d" % (Gmax, kappa)
+    s += "_mctherm_%d_mcsteps_%d_mcstddev_%.2f" % (mc_therm, mc_steps, mc_stddev)
+    s += "_hutchinson" if hutchinson else ""
+    s += ("_damping_%.5f_maxnorm_%.5f" % (damping, max_norm)) if sr else ("_lr_%.3f" % lr)
+    s += "_batch_%d_ndevices_%d_accsteps_%d" % (batch, num_devices, acc_steps)
+    return s
+
+
+def parse_run_dirname(path):
+    """Inverse of run_dirname for the fields the hot path needs -> dict(n, dim, rs, Theta, Emax, twist, depth, spsize,
+    tpsize, Gmax, kappa, mc_therm, mc_steps, mc_stddev, batch, num_devices, acc_steps)."""
+    import re
+    name = os.path.basename(os.path.normpath(path))
+    out = {}
+
+    def grab(key, pat, conv, field=None):
+        m = re.search(r"(?:^|_)%s_(%s)(?=_|$)" % (key, pat), name)
+        if m:
+            out[field or key] = conv(m.group(1))
+    num = r"-?\d+(?:\.\d+)?"
+    for key, conv in (("n", int), ("dim", int), ("rs", float), ("Theta", float), ("Emax", int), ("depth", int),
+                      ("spsize", int), ("tpsize", int), ("Gmax", int), ("kappa", int), ("batch", int), ("accsteps", int),
+                      ("ndevices", int), ("mctherm", int), ("mcsteps", int), ("mcstddev", float)):
+        grab(key, num, conv)
+    for old, new in (("accsteps", "acc_steps"), ("ndevices", "num_devices"), ("mctherm", "mc_therm"),
+                     ("mcsteps", "mc_steps"), ("mcstddev", "mc_stddev")):
+        if old in out:
+            out[new] = out.pop(old)
+    m = re.search(r"_twist((?:_%s)+?)_nlayers" % num, name)
+    if m:
+        out["twist"] = tuple(float(t) for t in m.group(1).strip("_").split("_"))
+    return out
+
+
+def ckpt_filename(epoch, path):
+    """src/checkpoint.py:7-8."""
+    return os.path.join(path, "epoch_%06d.pkl" % epoch)
+
+
+def pretrained_model_filename(freefermion_path):
+    """src/checkpoint.py:4-5."""
+    return os.path.join(freefermion_path, "params_van.pkl")
+
+
+# ----------------------------------------------------------------------------------------------------
+# checkpoints
+# ----------------------------------------------------------------------------------------------------
+
+
+class _Opaque(tuple):
+    """Stand-in for pickled objects of libraries that are not installed (optax optimiser states, haiku containers):
+    kept as an empty tuple so the dict round-trips; the hot path never looks inside `opt_state`."""
+
+    def __new__(cls, *a, **k):
+        return super().__new__(cls)
+
+    def __reduce__(self):
+        return (tuple, ())
+
+
+def _rebuild_jax_array(fun, args, arr_state, aval_state=None):
+    # jax pickles an Array as (numpy reconstruct fn, args, ndarray state, aval state): rebuild the ndarray, drop the aval
+    arr = fun(*args)
+    arr.__setstate__(arr_state)
+    return arr
+
+
+class _RefUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        root = module.split(".")[0]
+        if root == "jax" or root == "jaxlib":
+            return _rebuild_jax_array if name == "_reconstruct_array" else _Opaque
+        if root in ("optax", "haiku", "flax", "chex"):
+            return _Opaque
+        return super().find_class(module, name)
+
+
+def _numpyfy(t):
+    if isinstance(t, dict):
+        return {k: _numpyfy(v) for k, v in t.items()}
+    if isinstance(t, _Opaque):
+        return t
+    if isinstance(t, (list, tuple)):
+        return type(t)(_numpyfy(v) for v in t) if type(t) in (list, tuple) else t
+    if hasattr(t, "__array__"):
+        return np.asarray(t)
+    return t
+
+
+def load_data(filename):
+    """src/checkpoint.py:10-13 without jax/optax/haiku: returns the pickled object with every array as numpy.
+    For `epoch_*.pkl` that is {keys (ndev,2) u32, x (ndev,B/ndev,n,dim) f64, params_van, params_flow, opt_state}
+    (main.py:377-381); for `params_van.pkl` the VAN parameter dict."""
+    with open(filename, "rb") as f:
+        return _numpyfy(_RefUnpickler(f).load())
+
+
+def loads(buf):
+    return _numpyfy(_RefUnpickler(io.BytesIO(buf)).load())
+
+
+def save_data(data, filename):
+    """src/checkpoint.py:15-17.  Arrays are written as numpy (torch tensors are moved to host first), which the
+    reference's `pickle.load` + `src.shard` / `src.replicate` accept unchanged (main.py:218-223)."""
+    def host(t):
+        if isinstance(t, dict):
+            return {k: host(v) for k, v in t.items()}
+        if type(t) in (list, tuple):
+            return type(t)(host(v) for v in t)
+        if hasattr(t, "detach") and hasattr(t, "cpu"):
+            return t.detach().cpu().numpy()
+        return t
+    tmp = filename + ".tmp"
+    with open(tmp, "wb") as f:
+        pickle.dump(host(data), f)
+    os.replace(tmp, filename)
+
+
+def shard_walkers(x, rank, world_size):
+    """The walker shard of one rank.  The reference stores x as (ndev, B/ndev, n, dim) (main.py:236-238); the global
+    batch is its row-major flattening, and rank r of `world_size` takes the contiguous block r (main.py:234-238 with
+    ndev = world_size).  Re-sharding a checkpoint written with a different device count is therefore a reshape."""
+    x = np.asarray(x)
+    if x.ndim == 4:
+        x = x.reshape(-1, x.shape[2], x.shape[3])
+    if x.ndim != 3:
+        raise ValueError("x must be (ndev, B/ndev, n, dim) or (B, n, dim)")
+    B = x.shape[0]
+    if B % world_size != 0:
+        raise ValueError("Batch size must be divisible by the number of GPU devices. Got batch = %d for %d devices now."
+                         % (B, world_size))           # main.py:231-233
+    per = B // world_size
+    return np.ascontiguousarray(x[rank * per:(rank + 1) * per])
+
+
+def gather_walkers(shards):
+    """Inverse of shard_walkers for writing a checkpoint: list of per-rank (B/N, n, dim) -> (N, B/N, n, dim)."""
+    return np.stack([np.asarray(s) for s in shards], axis=0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# data.txt
+# ----------------------------------------------------------------------------------------------------
+_OBS = ("F", "E", "K", "V", "S")
+
+
+def observable_std(mean, mean2, batch, acc_steps):
+    """main.py:355-359."""
+    return float(np.sqrt((mean2 - mean ** 2) / (batch * acc_steps)))
+
+
+def format_data_line(epoch, *, F, F_std, E, E_std, K, K_std, V, V_std, S, S_std, accept_rate, rs):
+    """One line of data.txt (main.py:369-374): energies in Ry/rs^2 are divided by rs^2 here, as main.py does."""
+    r2 = rs ** 2
+    return ("%6d" + "  %.6f" * 10 + "  %.4f" + "\n") % (epoch, F / r2, F_std / r2, E / r2, E_std / r2, K / r2, K_std / r2,
+                                                        V / r2, V_std / r2, S, S_std, accept_rate)
+
+
+def read_data_txt(filename):
+    """-> dict of columns: epoch, F, F_std, E, E_std, K, K_std, V, V_std, S, S_std, accept_rate (as logged, i.e. /rs^2)."""
+    rows = np.loadtxt(filename, ndmin=2)
+    names = ["epoch"] + [n + s for n in _OBS for s in ("", "_std")] + ["accept_rate"]
+    if rows.shape[1] != len(names):
+        raise ValueError("%s: expected %d columns, found %d" % (filename, len(names), rows.shape[1]))
+    return {k: rows[:, i] for i, k in enumerate(names)}
