@@ -67,8 +67,9 @@ size_t sweep_smem_bytes(int n) {
     const int n8 = 8 * sweep_num_warps(n);
     const size_t fixed = (size_t)(16 * n8 * 4 + 256 + 4 * W_TOTAL + 16 * n8 + 8 * n8 + 64 * n8 + 144 * n8 + 160);
     const size_t jb = sizeof(float4) * n * pitch_B(n);
-    const size_t rt = sizeof(float) * n8 * 36 * 2;      // R|T rows; afterwards the LU pivot lines (<= rt for NW <= 8)
-    return fixed + jb + rt;
+    const size_t rt = sizeof(float) * n8 * 36 * 2;      // R|T rows; afterwards the LU pivot lines [2][NW][8 NW + 16] x 16 B
+    const size_t nw = n8 / 8, ln = 2 * nw * (8 * nw + 16) * 16;
+    return fixed + jb + (rt > ln ? rt : ln);
 }
 
 struct Smem {
@@ -554,7 +555,7 @@ sweep_kernel(const SweepParams p) {
             // Jacobian: J = I + (small) for any physical flow, so the fast path is an UNPIVOTED 2x2-block LU
             // (log|det J| = sum_k log|det P_kk|); multipliers and pivot determinants are monitored and an evaluation
             // that leaves the safe range is redone with the partially pivoted scalar LU below (use_pivot).
-            constexpr int MB = 2 * NW, LP = 4 * MB + 4;
+            constexpr int MB = 2 * NW, LP = 4 * MB + 16;   // lines are padded: tails are cut in chunks of 4 slots
             const int qbase = lane & ~3;
             if (warp == NW - 1) {        // mean backflow displacement (a pure phase of det D; keeps the phases small)
                 double mx = 0.0, my = 0.0;
@@ -601,7 +602,7 @@ sweep_kernel(const SweepParams p) {
                             bad |= (rv && row > k) && (fabsf(l00) + fabsf(l01) + fabsf(l10) + fabsf(l11)) > 4.f;
 #pragma unroll
                             for (int m = 0; m < MB; ++m) {
-                                if (4 * (base + m) >= n) break;                  // uniform: the live tail shrinks with base
+                                if ((m & 3) == 0 && 4 * (base + m) >= n) break;  // uniform, per chunk of 4 slots: the live tail shrinks
                                 const int j = 4 * (base + m) + q;
                                 if (sst == 3) {
                                     if (m >= 1) {
@@ -627,7 +628,7 @@ sweep_kernel(const SweepParams p) {
                                 const int nb = (k + 1) >> 2;
 #pragma unroll
                                 for (int m = 0; m < MB; ++m) {
-                                    if (4 * (nb + m) >= n) break;
+                                    if ((m & 3) == 0 && 4 * (nb + m) >= n) break;
                                     nxt[4 * (nb + m) + q] = Jr[m];
                                 }
                             }
@@ -730,31 +731,40 @@ sweep_kernel(const SweepParams p) {
                 double2* const dslots = reinterpret_cast<double2*>(s.Rbuf);       // [2][NW][LP]
                 bool done = !rv, singular = false;
                 double mypn = 1.0;
-                auto offer_publish = [&](int kn) {        // candidates for pivot column kn (held in slot 0 of quad lane kn&3)
+                unsigned wcand = 0u;                      // this warp's candidate key for the next pivot column
+                auto offer = [&](int kn) {                // candidates for pivot column kn (held in slot 0 of quad lane kn&3)
                     const float mag = (float)(fabs(Dr[0].x) + fabs(Dr[0].y));
                     const unsigned key = (done || q != (kn & 3)) ? 0u : ((__float_as_uint(mag) & ~0x3Fu) | (unsigned)row);
-                    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-                    if (lane == 0) s.redD[(kn & 1) * 8 + warp] = wmax;
-                    if ((wmax >> 6) != 0u && row == (int)(wmax & 0x3Fu)) {
+                    wcand = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0) s.redD[(kn & 1) * 8 + warp] = wcand;
+                };
+                auto publish = [&](int kn) {              // the warp's candidate row goes into the warp's own line slot
+                    if ((wcand >> 6) != 0u && row == (int)(wcand & 0x3Fu)) {
                         double2* slot = dslots + ((kn & 1) * NW + warp) * LP;
                         const int nb = kn >> 2;
 #pragma unroll
                         for (int m = 0; m < MB; ++m) {
-                            if (4 * (nb + m) >= n) break;
+                            if ((m & 3) == 0 && 4 * (nb + m) >= n) break;
                             slot[4 * (nb + m) + q] = Dr[m];
                         }
                     }
                 };
-                offer_publish(0);
+                if (tid < 16) s.redD[tid] = 0u;
+                __syncthreads();
+                offer(0);
+                publish(0);
                 __syncthreads();
                 for (int base = 0; 4 * base < n; ++base) {
 #pragma unroll
                     for (int sst = 0; sst < 4; ++sst) {
                         const int k = 4 * base + sst;
                         if (k >= n) break;
-                        unsigned gmax = s.redD[(k & 1) * 8];
-#pragma unroll
-                        for (int w = 1; w < NW; ++w) gmax = max(gmax, s.redD[(k & 1) * 8 + w]);
+                        unsigned gmax;
+                        {
+                            const uint4 ka = *reinterpret_cast<const uint4*>(s.redD + (k & 1) * 8);      // unused slots stay 0
+                            const uint4 kb = *reinterpret_cast<const uint4*>(s.redD + (k & 1) * 8 + 4);
+                            gmax = max(max(max(ka.x, ka.y), max(ka.z, ka.w)), max(max(kb.x, kb.y), max(kb.z, kb.w)));
+                        }
                         singular |= (gmax >> 6) == 0u;
                         const int pr = (int)(gmax & 0x3Fu);
                         const double2* cur = dslots + ((k & 1) * NW + (pr >> 3)) * LP;
@@ -773,7 +783,8 @@ sweep_kernel(const SweepParams p) {
                             const double lx = -(cx * ivx - cy * ivy), ly = -(cx * ivy + cy * ivx);   // l = -c / pivot
 #pragma unroll
                             for (int m = 0; m < MB; ++m) {
-                                if (4 * (base + m) >= n) break;
+                                if ((m & 3) == 0 && 4 * (base + m) >= n) break;
+                                if (m == 4) offer(k + 1);                       // column k+1 is final after the first chunk: REDUX overlaps the rest
                                 const int j = 4 * (base + m) + q;
                                 if (sst == 3) {
                                     if (m >= 1) {
@@ -791,8 +802,11 @@ sweep_kernel(const SweepParams p) {
                                     Dr[m] = v;
                                 }
                             }
+                            if (4 * (base + 4) >= n || MB <= 4) offer(k + 1);    // short tail: the loop left before slot 4
+                        } else {
+                            offer(k + 1);                                       // every row of this warp is finished: key 0
                         }
-                        offer_publish(k + 1);
+                        publish(k + 1);
                         __syncthreads();
                     }
                 }
