@@ -306,3 +306,32 @@ def test_large_wavevectors_use_the_staged_slater_path(cg, oracle):
     lp = cg.make_logp(kt, L)(x, p, si)
     ref = oracle["logpsi"].logp_batch(x, p, si, kt, L)
     assert np.abs(lp - ref).max() < RTOL * np.abs(ref).max(), np.abs(lp - ref).max()
+
+
+# ------------------------------------------------------------------ replay of a reference run (SURVEY §8 f/N1)
+def test_replay_checkpoint_tool(cg, cases, tmp_path):
+    """A run directory in the reference's on-disk format (main.py:194-206, 376-384), built from the shipped n=29 rs=1
+    walkers and trained parameters, replayed through the kernels by tools/replay_checkpoint.py: the data.txt line
+    parses, the accept rate matches the shipped log and V/rs^2 the shipped V within the statistical error."""
+    import json, os, subprocess, sys
+    from conftest import GOLDEN, ROOT
+    from coulombgas_b200 import interop
+    c = cases("n29_rs1")
+    pins = json.load(open(os.path.join(GOLDEN, "data_txt_pins.json")))["n29_rs1"]
+    f = interop.parse_run_dirname(pins["run"])
+    B = (c["x"].shape[0] // 8) * 8
+    f["batch"] = B
+    run = interop.run_dirname(str(tmp_path) + "/", nlayers=2, modelsize=16, nheads=4, nhidden=32, hutchinson=True, **f)
+    os.makedirs(run)
+    interop.save_data({"keys": np.zeros((8, 2), np.uint32), "x": c["x"][:B].reshape(8, B // 8, c["n"], 2),
+                       "params_van": {}, "params_flow": c["params"], "opt_state": ()}, interop.ckpt_filename(3000, run))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "replay_checkpoint.py"), run, "--acc-steps", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = out.stdout.strip().splitlines()[-1]
+    (tmp_path / "data.txt").write_text(line + "\n")
+    d = interop.read_data_txt(str(tmp_path / "data.txt"))
+    assert int(d["epoch"][0]) == 3000 and np.isnan(d["K"][0])
+    # ground-state occupations instead of VAN samples: same acceptance to a few percent, V within the error bars
+    assert abs(d["accept_rate"][0] - pins["accept_rate"]) < 0.08, (line, pins)
+    assert abs(d["V"][0] - pins["V"]) < 5 * np.hypot(d["V_std"][0], pins["V_std"]) + 0.02 * abs(pins["V"]), (line, pins)
