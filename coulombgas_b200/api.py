@@ -52,7 +52,9 @@ def kpoints(dim, Gmax):
     grids = np.meshgrid(*([rng] * dim))
     G = np.array([g.flatten() for g in grids]).T
     G2 = (G ** 2).sum(axis=-1)
-    return G[(G2 <= Gmax ** 2) * (G2 > 0)]
+    G = np.ascontiguousarray(G[(G2 <= Gmax ** 2) * (G2 > 0)])
+    G.setflags(write=False)           # a constant table (main.py:170); lets potential_energy skip re-hashing it
+    return G
 
 
 def madelung(dim, kappa, G):
@@ -271,14 +273,20 @@ def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
 # Ewald
 # ----------------------------------------------------------------------------------------------------
 _EWALD_CACHE = {}
+_EWALD_LAST = [None, None, None, None]       # (G object, kappa, device, tables): identity fast path for the hot loop
 
 
 def ewald_tables(G, kappa):
-    """Fold (G, kappa) into the merged reciprocal item table (cgb_ewald_prepare_host); cached per device."""
+    """Fold (G, kappa) into the merged reciprocal item table (cgb_ewald_prepare_host); cached per device.
+    The training loop passes the same constant `G` array every step (main.py:170): a repeated call with the
+    identical array object skips the content hash."""
+    dev = torch.cuda.current_device()
+    if G is _EWALD_LAST[0] and kappa == _EWALD_LAST[1] and dev == _EWALD_LAST[2]:
+        return _EWALD_LAST[3]
     Gh = np.ascontiguousarray(np.asarray(G.cpu() if isinstance(G, torch.Tensor) else G, dtype=np.int64))
     if Gh.ndim != 2 or Gh.shape[1] != 2:
         raise NotImplementedError("only dim=2 is supported (G must be (nG, 2))")
-    key = (Gh.tobytes(), float(kappa), torch.cuda.current_device())
+    key = (Gh.tobytes(), float(kappa), dev)
     if key not in _EWALD_CACHE:
         items = np.empty((Gh.shape[0], 4), dtype=np.float32)
         n_items, gmax = ctypes.c_int(), ctypes.c_int()
@@ -287,6 +295,8 @@ def ewald_tables(G, kappa):
                                          ctypes.byref(gmax)), "cgb_ewald_prepare_host")
         dev_items = torch.as_tensor(items[:n_items.value].copy()).to(_dev())
         _EWALD_CACHE[key] = (dev_items, n_items.value, gmax.value)
+    if isinstance(G, np.ndarray) and not G.flags.writeable:
+        _EWALD_LAST[:] = [G, kappa, dev, _EWALD_CACHE[key]]        # only immutable arrays qualify for the identity path
     return _EWALD_CACHE[key]
 
 

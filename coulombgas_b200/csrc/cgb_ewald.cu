@@ -2,102 +2,182 @@
 //
 // The reference evaluates  sum_G g_G sum_{i<j} cos(2 pi G.r_ij)  pairwise (O(|G| n^2)); here the same sum
 // is taken in structure-factor form  1/2 (|S(G)|^2 - n),  S(G) = sum_i e^{2 pi i G.u_i}  (O(|G| n)), with
-// e^{2 pi i G.u} = px_i[|Gx|] * py_i[|Gy|]^(*) from per-particle power tables kept in shared memory, and the
-// (Gx,Gy)/(Gx,-Gy)/(-G) quadruple sharing one set of four real accumulators (host-side merge in
-// cgb_ewald_prepare_host).  Real space: nearest image only, erfc(kappa d)/d (potential.py:45-50).
-// One CTA (128 threads) per walker, persistent over the batch.
+// e^{2 pi i G.u} = px_i[|Gx|] * py_i[|Gy|]^(*) from per-particle power tables, and the (Gx,Gy)/(Gx,-Gy)/(-G)
+// quadruple sharing one set of four real accumulators (host-side merge in cgb_ewald_prepare_host).
+// Real space: nearest image only, erfc(kappa d)/d (potential.py:45-50).
+//
+// One WARP per walker (persistent over the batch), no block barrier after the weight table is staged:
+//   * lane i builds the power tables of particles i, i+32: ONE sincospi per coordinate (phase reduced in float64,
+//     hi/lo corrected), higher harmonics by complex multiplication;
+//   * the reciprocal sum is a small complex matrix product  S+-(gx,gy) = sum_i px_i[gx] py_i[gy]^(*)  over the
+//     (gmax+1)^2 quadrant, register-tiled 2 x 4 per lane: per particle 3 broadcast LDS.128 feed 32 FFMA; the
+//     merged weights (w+, w-) sit in a dense CTA-shared table (zero outside the |G| <= Gmax disc);
+//   * the n(n-1)/2 real-space pairs are dealt round-robin to the lanes (triangular index decoded per pair).
 #include "cgb_common.cuh"
 #include "cgb_internal.h"
 
 namespace cgb {
 
-constexpr int EW_THREADS = 128;
+struct EwLay {                      // per-warp shared-memory slice (bytes), n particles, harmonics 0..gmax
+    int npx, npy, pitch_x, pitch_y, o_px, o_py, total;
+    __host__ __device__ EwLay(int n, int gmax) {
+        npx = (gmax + 2) & ~1;                 // px harmonics padded to a multiple of 2 (tile width in gx)
+        npy = (gmax + 4) & ~3;                 // py harmonics padded to a multiple of 4 (tile width in gy)
+        pitch_x = npx + 2;                     // float2 units; +2 keeps 16-byte alignment and spreads rows over the banks
+        pitch_y = npy + 2;
+        o_px = 16 * n;                         // double2 u[n] first
+        o_py = o_px + 8 * n * pitch_x;
+        total = (o_py + 8 * n * pitch_y + 15) & ~15;
+    }
+};
 
-__global__ void __launch_bounds__(EW_THREADS, 8) ewald_kernel(const EwaldParams p) {
+__device__ __forceinline__ float2 cmulf(const float2 a, const float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+__global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, tid = threadIdx.x, np1 = p.gmax + 1;
-    double* u = reinterpret_cast<double*>(smem_raw);                    // [n][2] reduced coordinates
-    float2* px = reinterpret_cast<float2*>(u + 2 * n);                  // [n][np1]
-    float2* py = px + n * np1;                                          // [n][np1]
-    __shared__ double red[EW_THREADS / 32];
+    const int n = p.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const EwLay L_(n, p.gmax);
+    const int tiles_x = L_.npx >> 1, tiles_y = L_.npy >> 2, ntiles = tiles_x * tiles_y;
+    // dense weights (w+, w-)[gx][gy] over the padded quadrant, CTA-shared
+    float2* const Wd = reinterpret_cast<float2*>(smem_raw);
+    const int wd_bytes = (8 * L_.npx * L_.npy + 15) & ~15;
+    for (int t = threadIdx.x; t < L_.npx * L_.npy; t += blockDim.x) Wd[t] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.n_items; t += blockDim.x) {
+        const float4 it = p.items[t];
+        Wd[(int)it.x * L_.npy + (int)it.y] = make_float2(0.5f * it.z, 0.5f * it.w);
+    }
+    __syncthreads();
+    unsigned char* const sm = smem_raw + wd_bytes + warp * L_.total;
+    double2* const u = reinterpret_cast<double2*>(sm);
+    float2* const px = reinterpret_cast<float2*>(sm + L_.o_px);
+    float2* const py = reinterpret_cast<float2*>(sm + L_.o_py);
     const double invL = 1.0 / p.L;
-    const float kap = (float)p.kappa;
+    const float kap = (float)p.kappa, fn = (float)n;
+    const int npairs = n * (n - 1) / 2;
+    const float tn1 = (float)(2 * n - 1);
 
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        __syncthreads();
-        for (int t = tid; t < 2 * n; t += EW_THREADS) {
-            double v = p.x[(size_t)b * 2 * n + t] * invL;               // x / L  (potential.py:77)
-            u[t] = v - floor(v);
+    for (int b = blockIdx.x * nwarps + warp; b < p.B; b += gridDim.x * nwarps) {
+        __syncwarp();
+        // ---- reduced coordinates and power tables e^{2 pi i g u}, g = 0..gmax (padding harmonics = 0)
+        for (int i = lane; i < n; i += 32) {
+            double2 xv = __ldg(reinterpret_cast<const double2*>(p.x) + (size_t)b * n + i);
+            xv.x *= invL; xv.y *= invL;                                   // x / L  (potential.py:77)
+            xv.x -= floor(xv.x); xv.y -= floor(xv.y);
+            u[i] = xv;
+#pragma unroll 1
+            for (int comp = 0; comp < 2; ++comp) {
+                const double uc = comp ? xv.y : xv.x;
+                const float uh = (float)uc, ul = (float)(uc - (double)uh);
+                float sn, cs;
+                sincospif(2.f * uh, &sn, &cs);
+                const float pl = 2.f * kPi * ul;                          // first-order hi/lo correction of the phase
+                const float2 p1 = make_float2(fmaf(-pl, sn, cs), fmaf(pl, cs, sn));
+                float2* row = comp ? (py + i * L_.pitch_y) : (px + i * L_.pitch_x);
+                const int np = comp ? L_.npy : L_.npx;
+                float2 pw = make_float2(1.f, 0.f);
+                for (int g = 0; g < np; g += 2) {
+                    const float2 a = g <= p.gmax ? pw : make_float2(0.f, 0.f);
+                    pw = cmulf(pw, p1);
+                    const float2 c = g + 1 <= p.gmax ? pw : make_float2(0.f, 0.f);
+                    pw = cmulf(pw, p1);
+                    *reinterpret_cast<float4*>(row + g) = make_float4(a.x, a.y, c.x, c.y);
+                }
+            }
         }
-        __syncthreads();
-        // power tables e^{2 pi i g u}, g = 0..gmax, phases reduced exactly in float64
-        for (int t = tid; t < 2 * n * np1; t += EW_THREADS) {
-            const int g = t % np1, c = t / np1;                          // c = particle*2 + comp
-            double ph = (double)g * u[c];
-            ph -= floor(ph);
-            float sn, cs;
-            sincospif(2.f * (float)ph, &sn, &cs);
-            ((c & 1) ? py : px)[(c >> 1) * np1 + g] = make_float2(cs, sn);
-        }
-        __syncthreads();
+        __syncwarp();
         float acc = 0.f;
-        // reciprocal space
-        for (int t = tid; t < p.n_items; t += EW_THREADS) {
-            const float4 it = p.items[t];
-            const int gx = (int)it.x, gy = (int)it.y;
-            float ac = 0.f, bd = 0.f, ad = 0.f, bc = 0.f;
-#pragma unroll 4
+        // ---- reciprocal space: 2 x 4 register tile of (gx, gy) per lane
+        for (int tile = lane; tile < ntiles; tile += 32) {
+            const int tx = tile / tiles_y, ty = tile - tx * tiles_y;
+            const float4* pxa = reinterpret_cast<const float4*>(px + 2 * tx);
+            const float4* pya = reinterpret_cast<const float4*>(py + 4 * ty);
+            float ac[2][4], bd[2][4], ad[2][4], bc[2][4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { ac[a][c] = 0.f; bd[a][c] = 0.f; ad[a][c] = 0.f; bc[a][c] = 0.f; }
+#pragma unroll 2
             for (int i = 0; i < n; ++i) {
-                const float2 a = px[i * np1 + gx], c = py[i * np1 + gy];
-                ac = fmaf(a.x, c.x, ac); bd = fmaf(a.y, c.y, bd);
-                ad = fmaf(a.x, c.y, ad); bc = fmaf(a.y, c.x, bc);
+                const float4 xa = pxa[i * (L_.pitch_x >> 1)];
+                const float4 y0 = pya[i * (L_.pitch_y >> 1)], y1 = pya[i * (L_.pitch_y >> 1) + 1];
+                const float xr[2] = {xa.x, xa.z}, xi[2] = {xa.y, xa.w};
+                const float yr[4] = {y0.x, y0.z, y1.x, y1.z}, yi[4] = {y0.y, y0.w, y1.y, y1.w};
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        ac[a][c] = fmaf(xr[a], yr[c], ac[a][c]); bd[a][c] = fmaf(xi[a], yi[c], bd[a][c]);
+                        ad[a][c] = fmaf(xr[a], yi[c], ad[a][c]); bc[a][c] = fmaf(xi[a], yr[c], bc[a][c]);
+                    }
             }
-            const float spr = ac - bd, spi = ad + bc, smr = ac + bd, smi = bc - ad;
-            const float fn = (float)n;
-            acc = fmaf(0.5f * it.z, fmaf(spr, spr, spi * spi) - fn, acc);
-            acc = fmaf(0.5f * it.w, fmaf(smr, smr, smi * smi) - fn, acc);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float2 w = Wd[(2 * tx + a) * L_.npy + 4 * ty + c];
+                    const float spr = ac[a][c] - bd[a][c], spi = ad[a][c] + bc[a][c];
+                    const float smr = ac[a][c] + bd[a][c], smi = bc[a][c] - ad[a][c];
+                    acc = fmaf(w.x, fmaf(spr, spr, spi * spi) - fn, acc);
+                    acc = fmaf(w.y, fmaf(smr, smr, smi * smi) - fn, acc);
+                }
         }
-        // real space, nearest image (potential.py:45-50)
-        for (int t = tid; t < n * n; t += EW_THREADS) {
-            const int i = t / n, j = t % n;
-            if (i < j) {
-                double dx = u[2 * i] - u[2 * j], dy = u[2 * i + 1] - u[2 * j + 1];
-                dx -= rint(dx);
-                dy -= rint(dy);
-                const float fx = (float)dx, fy = (float)dy;
-                const float d2 = fmaf(fx, fx, fy * fy);
-                const float rd = rsqrtf(d2);
-                acc = fmaf(erfcf(kap * (d2 * rd)), rd, acc);
-            }
+        // ---- real space, nearest image (potential.py:45-50): pair index q -> (i < j), row i starts at i(2n-1-i)/2
+        for (int q = lane; q < npairs; q += 32) {
+            int i = (int)((tn1 - sqrtf(fmaf(tn1, tn1, -8.f * (float)q))) * 0.5f);
+            i = max(0, min(i, n - 2));
+            int r0 = (i * (2 * n - 1 - i)) >> 1;
+            if (r0 > q) { --i; r0 = (i * (2 * n - 1 - i)) >> 1; }
+            else if (q - r0 >= n - 1 - i) { r0 += n - 1 - i; ++i; }
+            const int j = i + 1 + (q - r0);
+            const double2 ui = u[i], uj = u[j];
+            double dx = ui.x - uj.x, dy = ui.y - uj.y;
+            dx -= rint(dx);
+            dy -= rint(dy);
+            const float fx = (float)dx, fy = (float)dy;
+            const float d2 = fmaf(fx, fx, fy * fy);
+            const float rd = rsqrtf(d2);
+            acc = fmaf(erfcf(kap * (d2 * rd)), rd, acc);
         }
         double a = (double)acc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if ((tid & 31) == 0) red[tid >> 5] = a;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < EW_THREADS / 32; ++w) tot += red[w];
+        if (lane == 0) {
             const double g0 = -2.0 * sqrt(3.14159265358979323846) / p.kappa;       // potential.py:59
-            tot += g0 * (0.5 * n * (n - 1));                                      // potential.py:62
-            p.out[b] = 2.0 * p.rs * invL * tot;                                   // potential.py:77
+            a += g0 * (0.5 * n * (n - 1));                                        // potential.py:62
+            p.out[b] = 2.0 * p.rs * invL * a;                                     // potential.py:77
         }
     }
 }
 
 int launch_ewald(const EwaldParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(double) * 2 * p.n + sizeof(float2) * 2 * p.n * (p.gmax + 1);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ewald_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    const EwLay L_(p.n, p.gmax);
+    const int wd_bytes = (8 * L_.npx * L_.npy + 15) & ~15;
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ewald_kernel, EW_THREADS, smem);
-    if (occ < 1) occ = 1;
-    const int grid = p.B < sms * occ ? p.B : sms * occ;
-    ewald_kernel<<<grid, EW_THREADS, smem, st>>>(p);
+    // warps per CTA: 8 while three CTAs still fit one SM's shared memory, fewer for large n / gmax; small batches
+    // use smaller CTAs so that the walkers spread over all SMs
+    int wpc = 8;
+    while (wpc > 1 && (size_t)wd_bytes + (size_t)wpc * L_.total > 72 * 1024) wpc >>= 1;
+    while (wpc > 1 && (long long)p.B < (long long)sms * wpc) wpc >>= 1;
+    const size_t smem = (size_t)wd_bytes + (size_t)wpc * L_.total;
+    if (smem > 227 * 1024) return CGB_E_UNSUPPORTED;
+    // attribute + occupancy queries are cached per (device, shape): the steady-state call is one launch
+    static thread_local struct { int dev; size_t smem; int wpc; int occ; } cache = {-1, 0, 0, 0};
+    if (cache.dev != dev || cache.smem != smem || cache.wpc != wpc) {
+        cudaError_t e = cudaFuncSetAttribute(ewald_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ewald_kernel, wpc * 32, smem);
+        if (occ < 1) occ = 1;
+        cache = {dev, smem, wpc, occ};
+    }
+    occ = cache.occ;
+    const long long need = ((long long)p.B + wpc - 1) / wpc;
+    const int grid = (int)(need < (long long)sms * occ ? need : (long long)sms * occ);
+    ewald_kernel<<<grid, wpc * 32, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 
