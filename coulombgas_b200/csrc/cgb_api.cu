@@ -108,12 +108,15 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
         p.ws_logp = (double*)(ws + o); o += ws_round(sizeof(double) * (size_t)B);
         p.ws_nacc = (int*)(ws + o);
     }
-    // kernel choice: the warp-per-walker kernel (cgb_wsweep.cu) for the instantiated n <= 32 shapes, the
-    // CTA-per-walker kernel (cgb_sweep.cu) otherwise.  CGB_SWEEP_KERNEL=cta|warp overrides (debug / A-B timing).
+    // kernel choice.  Throughput: the warp-per-walker kernel (cgb_wsweep.cu) for the instantiated n <= 32 shapes.
+    // Latency: when the batch cannot fill the machine with one warp per walker (B200: 148 SMs x 12 warps), the
+    // CTA-per-walker kernel (cgb_sweep.cu; 4 lanes per particle) finishes a sweep sooner -- measured cross-over
+    // (tools/time_small_batches.py): B ~ 700 at n = 13, B ~ 400 at n = 29.  Every other n uses the CTA kernel.
+    // CGB_SWEEP_KERNEL=cta forces the CTA kernel, =warp prefers the warp kernel wherever an instance exists.
     const char* kk = getenv("CGB_SWEEP_KERNEL");
-    bool use_warp = wsweep_supported(n);
+    bool use_warp = wsweep_supported(n) && B > (n <= 16 ? 768 : 384);
     if (kk && kk[0] == 'c') use_warp = false;
-    if (kk && kk[0] == 'w' && !wsweep_supported(n)) return CGB_E_UNSUPPORTED;
+    if (kk && kk[0] == 'w') use_warp = wsweep_supported(n);
     if (use_warp) return launch_wsweep(p, ws + WS_WCONST, st);
     int rc = launch_prep_params(params, (float*)workspace, st);
     if (rc) return rc;

@@ -23,6 +23,17 @@ def cg():
     return cg
 
 
+@pytest.fixture(autouse=True, params=["auto", "warp"])
+def sweep_kernel_choice(request, monkeypatch):
+    """Every test runs twice: with the library's own kernel choice (small test batches go to the CTA-per-walker
+    kernel) and with the warp-per-walker kernel preferred wherever it has an instance (n = 13, 29)."""
+    if request.param == "warp":
+        monkeypatch.setenv("CGB_SWEEP_KERNEL", "warp")
+    else:
+        monkeypatch.delenv("CGB_SWEEP_KERNEL", raising=False)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def oracle():
     from oracle import logpsi, mcmc, potential
@@ -279,6 +290,7 @@ def test_ready_queue_any_batch_size(cg, cases, B, monkeypatch):
     x0 = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2))
     si = np.tile(c["state_idx"], (reps, 1))[:B]
     logp = cg.make_logp(c["ktable"], c["L"])
+    monkeypatch.setenv("CGB_SWEEP_KERNEL", "warp")
     xw, accw, trw = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, return_trace=True)
     monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
     xc, accc, trc = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, return_trace=True)
