@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
         // ---------------- pass 2 + 3: Jacobian blocks  J_ik = Q_i E_ik + R_i F_ik + T_i H_k  -> staging -----------
         {
             float R[2][16], T[2][16];
+            __syncwarp();                    // padding lanes (>= N) mirror row N-1, written by lane N-1 just above
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 const float* sc = sScr + kself * 68 + 4 * c4;

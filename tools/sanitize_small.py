@@ -10,8 +10,11 @@ for tag, B in (("n13_rs10", 3), ("n29_rs1", 3), ("n49_rs0.5", 2), ("n57_rs0.25",
     c = load_case(tag)
     logp = cg.make_logp(c["ktable"], c["L"])
     x, si = c["x"][:B].copy(), c["state_idx"][:B]
-    lp = logp(x, c["params"], si)
-    xs, acc = cg.mcmc(logp.bind(c["params"], si), x, 5, 3, 0.1)
+    for kern in ("cta", "warp"):                  # both sweep kernels where n has a warp instance
+        os.environ["CGB_SWEEP_KERNEL"] = kern
+        lp = logp(x, c["params"], si)
+        xs, acc = cg.mcmc(logp.bind(c["params"], si), x.copy(), 5, 3, 0.1)
+    del os.environ["CGB_SWEEP_KERNEL"]
     os.environ["CGB_FORCE_PIVOT"] = "1"
     lp2 = logp(x, c["params"], si)
     del os.environ["CGB_FORCE_PIVOT"]
