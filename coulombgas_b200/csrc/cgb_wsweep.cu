@@ -996,7 +996,8 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-bool wsweep_supported(int n) { return n == 13 || n == 29; }
+// instantiated shapes: the closed shells of the 2D plane-wave lattice up to one warp (the reference's runs use 13, 29)
+bool wsweep_supported(int n) { return n == 9 || n == 13 || n == 21 || n == 25 || n == 29; }
 
 template <int N>
 static int launch_wn(const SweepParams& p, cudaStream_t st) {
@@ -1044,7 +1045,10 @@ int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
     e = cudaMemsetAsync(p.done, 0, sizeof(int) * (size_t)p.B, st);
     if (e != cudaSuccess) return (int)e;
     switch (p.n) {
+        case 9: return launch_wn<9>(p, st);
         case 13: return launch_wn<13>(p, st);
+        case 21: return launch_wn<21>(p, st);
+        case 25: return launch_wn<25>(p, st);
         case 29: return launch_wn<29>(p, st);
         default: return CGB_E_UNSUPPORTED;
     }

@@ -17,7 +17,7 @@
  *     only, no allocation, no synchronisation, no host-side mutable state (one call per stream at a time
  *     per workspace); the caller owns every buffer; workspace size comes from the *_workspace_bytes(B, n)
  *     query and grows with the batch (ready queue + per-walker scheduler state of the sweep kernel).
- *     The sweep kernel for n = 13, 29 keeps its weights in a per-device __constant__ block that every call
+ *     The warp-per-walker sweep kernel (n = 9, 13, 21, 25, 29) keeps its weights in a per-device __constant__ block that every call
  *     refreshes stream-ordered: sweeps with DIFFERENT parameters must not overlap on different streams of
  *     one device (same parameters, or one stream per device as under jax.pmap, is always fine).
  *   - I/O buffers are float64 (the reference runs with jax_enable_x64, main.py:2-3); internal arithmetic is

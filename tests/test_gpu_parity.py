@@ -122,7 +122,7 @@ def test_logp_general_n_and_weights(cg, oracle):
     from oracle import flow as oflow, tables
     rng = np.random.default_rng(3)
     kt, _ = tables.ktable(2, 49, (0.25, 0.25))
-    for n, std in ((2, 0.3), (3, 0.01), (8, 0.3), (9, 0.2), (16, 0.3), (17, 0.3), (32, 0.2), (33, 0.2), (40, 0.1),
+    for n, std in ((2, 0.3), (3, 0.01), (8, 0.3), (9, 0.2), (16, 0.3), (17, 0.3), (21, 0.2), (25, 0.2), (32, 0.2), (33, 0.2), (40, 0.1),
                    (48, 0.2), (56, 0.1), (64, 0.2)):
         L = float(np.sqrt(np.pi * n))
         p = oflow.init_params(2, 16, 16, 2, seed=n, stddev=std)
@@ -300,6 +300,33 @@ def test_ready_queue_any_batch_size(cg, cases, B, monkeypatch):
     assert np.abs(xw[same] - xc[same]).max() < 1e-12
     assert np.array_equal(trw["naccept"][same], trc["naccept"][same])
     assert np.abs(trw["logp"][same] - trc["logp"][same]).max() < RTOL * np.abs(trc["logp"]).max()
+
+
+@pytest.mark.parametrize("n", [9, 21, 25])
+def test_other_warp_kernel_instances(cg, oracle, n, monkeypatch):
+    """The warp-per-walker kernel is also instantiated for the other 2D closed shells below one warp (n = 9, 21, 25):
+    log p against the oracle and 8-step Metropolis chains against the CTA-per-walker kernel on the same Philox streams."""
+    from oracle import flow as oflow, tables
+    rng = np.random.default_rng(100 + n)
+    kt, _ = tables.ktable(2, 25, (0.25, 0.25))
+    L, B, S = float(np.sqrt(np.pi * n)), 40, 8
+    p = oflow.init_params(2, 16, 16, 2, seed=n, stddev=0.2)
+    p = {k: {"w": v["w"], "b": rng.normal(0, 0.1, v["b"].shape)} for k, v in p.items()}
+    x0 = rng.uniform(0, L, (B, n, 2))
+    si = np.stack([np.sort(rng.choice(kt.shape[0], n, replace=False)) for _ in range(B)]).astype(np.int32)
+    logp = cg.make_logp(kt, L)
+    monkeypatch.setenv("CGB_SWEEP_KERNEL", "warp")
+    lp = logp(x0, p, si)
+    ref = oracle["logpsi"].logp_batch(x0[:6], p, si[:6], kt, L)
+    assert np.abs(lp[:6] - ref).max() < RTOL * max(1.0, np.abs(ref).max())
+    xw, accw, trw = cg.mcmc(logp.bind(p, si), x0.copy(), 7, S, 0.1, return_trace=True)
+    monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
+    lpc = logp(x0, p, si)
+    assert np.abs(lp - lpc).max() < RTOL * max(1.0, np.abs(lpc).max())
+    xc, accc, trc = cg.mcmc(logp.bind(p, si), x0.copy(), 7, S, 0.1, return_trace=True)
+    same = (trw["accept"] == trc["accept"]).all(axis=0)
+    assert (~same).sum() <= 1, "chains diverged on %d of %d walkers" % ((~same).sum(), B)
+    assert np.abs(xw[same] - xc[same]).max() < 1e-12
 
 
 def test_large_wavevectors_use_the_staged_slater_path(cg, oracle):
