@@ -12,7 +12,10 @@ def _make_jnp():
                  "zeros", "ones", "arange", "sqrt", "floor", "rint", "abs", "triu_indices", "allclose",
                  "float64", "int32", "int64", "complex128", "sum", "mean", "clip", "tile", "asarray"):
         setattr(jnp, name, getattr(np, name))
+    for name in ("tril", "vstack", "tanh", "einsum", "reshape", "argmax", "max", "float32", "ones_like", "ndarray"):
+        setattr(jnp, name, getattr(np, name))
     jnp.array = lambda a, dtype=None: np.array(a, dtype=dtype)
+    jnp.zeros = lambda shape, dtype=None: np.zeros(shape, dtype=dtype or np.float64).view(_AtArray)
     jnp.alltrue = np.all
     linalg = types.ModuleType("jax.numpy.linalg")
 
@@ -27,6 +30,33 @@ def _make_jnp():
     linalg.inv = np.linalg.inv
     jnp.linalg = linalg
     return jnp
+
+
+class _AtArray(np.ndarray):
+    """ndarray with the functional-update accessor `a.at[idx].set(v)` (src/sampler.py:36-37)."""
+
+    @property
+    def at(self):
+        arr = self
+
+        class _At:
+            def __getitem__(self, idx):
+                class _Ref:
+                    def set(self, v):
+                        out = np.array(arr, copy=True).view(_AtArray)
+                        out[idx] = v
+                        return out
+                return _Ref()
+        return _At()
+
+
+def _log_softmax(x, axis=-1):
+    m = np.max(x, axis=axis, keepdims=True)
+    return x - (m + np.log(np.sum(np.exp(x - m), axis=axis, keepdims=True)))
+
+
+def _softmax(x, axis=-1):
+    return np.exp(_log_softmax(x, axis))
 
 
 # ----------------------------------------------------------------------------- jax core
@@ -141,6 +171,12 @@ class _Random(types.ModuleType):
         self.log.append(("uniform", v))
         return v
 
+    def categorical(self, key, logits, axis=-1):
+        """jax.random.categorical = argmax(logits + Gumbel noise); the noise is logged for the golden generators."""
+        g = self._rng(key).gumbel(size=np.shape(logits))
+        self.log.append(("gumbel", g))
+        return np.argmax(np.asarray(logits) + g, axis=axis)
+
 
 # ----------------------------------------------------------------------------- haiku
 def _make_haiku(jax_random):
@@ -241,8 +277,56 @@ def _make_haiku(jax_random):
             finally:
                 state["params"], state["mode"] = None, None
 
+    class VarianceScaling:
+        def __init__(self, scale=1.0, mode="fan_in", distribution="truncated_normal"):
+            self.scale, self.mode = scale, mode
+
+        def __call__(self, shape, rng):
+            fan = shape[0] if self.mode == "fan_in" else shape[-1]
+            return np.sqrt(self.scale / max(1.0, fan)) * rng.standard_normal(shape)
+
+    class TruncatedNormal:
+        def __init__(self, stddev=1.0, mean=0.0):
+            self.stddev, self.mean = stddev, mean
+
+        def __call__(self, shape, rng):
+            return self.mean + self.stddev * np.clip(rng.standard_normal(shape), -2, 2)
+
+    def get_parameter(name, shape, dtype=None, init=None):
+        mod = state["stack"][-1][0]
+        if state["mode"] == "init" and name not in state["params"].setdefault(mod, {}):
+            state["params"][mod][name] = init(tuple(shape), state["rng"])
+        return state["params"][mod][name]
+
+    class MultiHeadAttention(Module):
+        """dm-haiku's hk.MultiHeadAttention restated from its published algorithm (the library is not installed):
+        per-head `query`/`key`/`value` projections, logits q.k/sqrt(key_size), masked entries -> -1e30, softmax over
+        keys, heads concatenated, final `linear` projection to model_size = num_heads * key_size."""
+
+        def __init__(self, num_heads, key_size, w_init_scale=None, value_size=None, model_size=None, name=None):
+            super().__init__(name=name)
+            self.num_heads, self.key_size = num_heads, key_size
+            self.value_size = value_size or key_size
+            self.model_size = model_size or key_size * num_heads
+            self.w_init = VarianceScaling(w_init_scale if w_init_scale is not None else 1.0)
+
+        def __call__(self, query, key, value, mask=None):
+            def proj(x, size, name):
+                y = Linear(self.num_heads * size, w_init=self.w_init, name=name)(x)
+                return y.reshape(x.shape[:-1] + (self.num_heads, size))
+            q, k, v = proj(query, self.key_size, "query"), proj(key, self.key_size, "key"), proj(value, self.value_size, "value")
+            logits = np.einsum("...thd,...Thd->...htT", q, k) / np.sqrt(self.key_size)
+            if mask is not None:
+                logits = np.where(mask, logits, -1e30)
+            w = _softmax(logits)
+            att = np.einsum("...htT,...Thd->...thd", w, v)
+            att = att.reshape(query.shape[:-1] + (-1,))
+            return Linear(self.model_size, w_init=self.w_init)(att)
+
     inits = types.ModuleType("haiku.initializers")
     inits.RandomNormal = RandomNormal
+    inits.VarianceScaling, inits.TruncatedNormal = VarianceScaling, TruncatedNormal
+    hk.MultiHeadAttention, hk.get_parameter = MultiHeadAttention, get_parameter
     hk.Module, hk.Linear, hk.initializers, hk.transform = Module, Linear, inits, Transformed
     return hk
 
@@ -258,7 +342,7 @@ def install():
     jnp = _make_jnp()
     jax.numpy = jnp
     jax.random = _Random()
-    nn = types.ModuleType("jax.nn"); nn.softplus = _softplus; jax.nn = nn
+    nn = types.ModuleType("jax.nn"); nn.softplus = _softplus; nn.log_softmax = _log_softmax; nn.softmax = _softmax; jax.nn = nn
     lax = types.ModuleType("jax.lax")
     lax.fori_loop = _fori_loop
     lax.pmean = lambda x, axis_name=None: x       # one device
@@ -274,6 +358,7 @@ def install():
     jax.pmap = _pmap
     jax.jit = _jit
     jax.tree_map = _tree_map
+    jax.grad = lambda f, *a, **k: (lambda *aa, **kk: (_ for _ in ()).throw(NotImplementedError("grad is not part of the stand-in")))
     jax.device_count = lambda: 1
     hk = _make_haiku(jax.random)
     for name, mod in {"jax": jax, "jax.numpy": jnp, "jax.random": jax.random, "jax.nn": nn, "jax.lax": lax,
