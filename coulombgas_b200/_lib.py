@@ -34,9 +34,13 @@ def _load():
                                          vp, vp, vp, vp, vp, sz]
     lib.cgb_ewald_f64io.argtypes = [vp, vp, i32, i32, f64, f64, f64, vp, i32, i32, vp]
     lib.cgb_microbench.argtypes = [vp, i32, i32, i32, vp]
+    lib.cgb_van_nparams.argtypes = [i32]
+    lib.cgb_van_nparams.restype = sz
+    lib.cgb_van_sample_f64io.argtypes = [vp, vp, sz, vp, i32, i32, i32, vp, u64, vp, vp, vp]
+    lib.cgb_van_logprob_f64io.argtypes = [vp, vp, sz, vp, i32, i32, i32, vp, vp, vp]
     for f in ("cgb_ktable_twist_host", "cgb_ewald_prepare_host", "cgb_logp_workspace_bytes",
               "cgb_mcmc_workspace_bytes", "cgb_logp_f64io", "cgb_mcmc_sweep_f64io", "cgb_ewald_f64io",
-              "cgb_microbench"):
+              "cgb_microbench", "cgb_van_sample_f64io", "cgb_van_logprob_f64io"):
         getattr(lib, f).restype = i32
     return lib
 
@@ -45,7 +49,7 @@ lib = _load()
 
 EXPORTS = ("cgb_abi_version", "cgb_error_string", "cgb_ktable_twist_host", "cgb_ewald_prepare_host",
            "cgb_logp_workspace_bytes", "cgb_mcmc_workspace_bytes", "cgb_logp_f64io", "cgb_mcmc_sweep_f64io",
-           "cgb_ewald_f64io", "cgb_microbench")
+           "cgb_ewald_f64io", "cgb_microbench", "cgb_van_nparams", "cgb_van_sample_f64io", "cgb_van_logprob_f64io")
 
 
 def check(rc, what):

@@ -270,6 +270,121 @@ def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
 
 
 # ----------------------------------------------------------------------------------------------------
+# autoregressive momentum sampler (SURVEY §8 f/N2)
+# ----------------------------------------------------------------------------------------------------
+def pack_van_params(params_van, nlayers=2, prefix="transformer"):
+    """haiku dict of src/autoregressive.py:Transformer (modules `transformer`, `transformer/embedding_mlp`,
+    `transformer/layer{i}_attn/{query,key,value,linear}`, `transformer/layer{i}_mlp/{linear,linear_1}`,
+    `transformer/output_mlp`) -> the flat float64 vector of include/cgb200.h (cgb_van_*).  Flat vectors pass through."""
+    if isinstance(params_van, torch.Tensor):
+        return params_van.reshape(-1).to(torch.float64)
+    if isinstance(params_van, np.ndarray):
+        return np.ascontiguousarray(params_van.reshape(-1), dtype=np.float64)
+    parts = [np.asarray(params_van[prefix]["x1hat"], dtype=np.float64).ravel()]
+
+    def wb(name):
+        parts.append(np.asarray(params_van[name]["w"], dtype=np.float64).ravel())
+        parts.append(np.asarray(params_van[name]["b"], dtype=np.float64).ravel())
+    wb(prefix + "/embedding_mlp")
+    for i in range(nlayers):
+        for leaf in ("query", "key", "value", "linear"):
+            wb("%s/layer%d_attn/%s" % (prefix, i, leaf))
+        wb("%s/layer%d_mlp/linear" % (prefix, i))
+        wb("%s/layer%d_mlp/linear_1" % (prefix, i))
+    wb(prefix + "/output_mlp")
+    return np.concatenate(parts)
+
+
+@dataclasses.dataclass
+class ExplicitGumbel:
+    """Parity-mode `key` of the sampler: the Gumbel noise jax.random.categorical would add to the masked logits of
+    every draw (src/sampler.py:36-37), shape (batch, n, num_states)."""
+    noise: object
+
+
+class VanSampler:
+    """`sampler` / `log_prob` of make_autoregressive_sampler (src/sampler.py:3-49) on the GPU."""
+
+    def __init__(self, sp_indices, n, num_states):
+        kt = np.ascontiguousarray(np.asarray(sp_indices, dtype=np.float64))
+        if kt.shape != (num_states, 2):
+            raise ValueError("sp_indices must be (num_states, 2): only dim=2 is supported")
+        self.ktable_host, self.n, self.M = kt, int(n), int(num_states)
+        self.nparams = int(lib.cgb_van_nparams(self.M))
+        self._kt = {}
+
+    def _ktable(self):
+        d = torch.cuda.current_device()
+        if d not in self._kt:
+            self._kt[d] = torch.as_tensor(self.ktable_host).to(_dev())
+        return self._kt[d]
+
+    def _params(self, params):
+        pd, _ = _to_dev(pack_van_params(params), torch.float64)
+        if pd.numel() != self.nparams:
+            raise ValueError("unsupported VAN shape: expected %d parameters (nlayers=2, modelsize=16, nheads=4, nhidden=32, "
+                             "num_states=%d), got %d" % (self.nparams, self.M, pd.numel()))
+        return pd
+
+    def sampler(self, params, key, batch, return_log_prob=False, return_logits=False):
+        """src/sampler.py:30-38: (batch, n) int32 strictly increasing state indices.  key: int / (2,) uint32 -> in-kernel
+        Philox; ExplicitGumbel -> parity mode.  Results are CUDA tensors."""
+        pd = self._params(params)
+        B = int(batch)
+        g, seed = None, 0
+        if isinstance(key, ExplicitGumbel):
+            g, _ = _to_dev(key.noise, torch.float64)
+            if tuple(g.shape) != (B, self.n, self.M):
+                raise ValueError("ExplicitGumbel noise must be (batch, n, num_states)")
+        else:
+            seed = _seed_of(key)
+        dev = pd.device
+        out = torch.empty((B, self.n), dtype=torch.int32, device=dev)
+        lp = torch.empty(B, dtype=torch.float64, device=dev) if return_log_prob else None
+        lg = torch.empty((B, self.n, self.M), dtype=torch.float64, device=dev) if return_logits else None
+        check(lib.cgb_van_sample_f64io(_stream(), _ptr(pd), self.nparams, _ptr(self._ktable()), self.M, self.n, B, _ptr(g),
+                                       seed, _ptr(out), _ptr(lp), _ptr(lg)), "cgb_van_sample_f64io")
+        res = [out] + ([lp] if return_log_prob else []) + ([lg] if return_logits else [])
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def log_prob(self, params, state_indices, return_logits=False):
+        """vmap(log_prob_novmap, (None, 0)) of main.py:108 / src/sampler.py:40-44: (batch, n) -> (batch,)."""
+        pd = self._params(params)
+        sd, was_np = _to_dev(state_indices, torch.int32)
+        if sd.ndim != 2 or sd.shape[1] != self.n:
+            raise ValueError("state_indices must be (batch, n)")
+        B = int(sd.shape[0])
+        lp = torch.empty(B, dtype=torch.float64, device=pd.device)
+        lg = torch.empty((B, self.n, self.M), dtype=torch.float64, device=pd.device) if return_logits else None
+        check(lib.cgb_van_logprob_f64io(_stream(), _ptr(pd), self.nparams, _ptr(self._ktable()), self.M, self.n, B, _ptr(sd),
+                                        _ptr(lp), _ptr(lg)), "cgb_van_logprob_f64io")
+        if was_np:
+            lp, lg = lp.cpu().numpy(), (lg.cpu().numpy() if lg is not None else None)
+        return (lp, lg) if return_logits else lp
+
+
+def make_autoregressive_sampler(sp_indices, n, num_states, nlayers=2, modelsize=16, nheads=4, nhidden=32):
+    """src/sampler.py:3 with `network` = the Transformer of src/autoregressive.py at the reference's default shape
+    (main.py:24-27, 96-99).  Returns (sampler(params, key, batch), log_prob(params, state_indices))."""
+    if (nlayers, modelsize, nheads, nhidden) != (2, 16, 4, 32):
+        raise NotImplementedError("the VAN kernel is built for nlayers=2, modelsize=16, nheads=4, nhidden=32")
+    v = VanSampler(sp_indices, n, num_states)
+    return v.sampler, v.log_prob
+
+
+def sample_stateindices_and_x(key, sampler, params_van, logp, x, params_flow, mc_steps, mc_stddev, L):
+    """src/VMC.py:8-25 for THIS process's shard (one process per GPU replaces jax.pmap): key split (VMC.py:20), VAN draw of
+    the occupied orbitals (VMC.py:22), Metropolis sweep (VMC.py:23), wrap (VMC.py:24), cross-device mean of the accept rate
+    (MCMC.py:39).  `key` is an integer; returns (key', state_indices, x, accept_rate) like the reference."""
+    seed = _seed_of(key)
+    mix = lambda s, c: (s * 6364136223846793005 + c) & 0xFFFFFFFFFFFFFFFF
+    key_next, key_state, key_mcmc = mix(seed, 1442695040888963407), mix(seed, 0x9E3779B97F4A7C15), mix(seed, 0xD1B54A32D192ED03)
+    state_indices = sampler(params_van, key_state, int(x.shape[0]))
+    _, x, rate = sample_x(key_mcmc, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L)
+    return key_next, state_indices, x, rate
+
+
+# ----------------------------------------------------------------------------------------------------
 # Ewald
 # ----------------------------------------------------------------------------------------------------
 _EWALD_CACHE = {}

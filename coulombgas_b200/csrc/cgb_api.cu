@@ -155,6 +155,34 @@ int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, doubl
     return launch_ewald(p, (cudaStream_t)stream);
 }
 
+size_t cgb_van_nparams(int M) { return M > 0 ? van_nparams(M) : 0; }
+
+static int run_van(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n, int B,
+                   const int32_t* state_in, const double* gumbel, uint64_t seed, int32_t* out_state, double* out_logprob,
+                   double* out_logits) {
+    if (B == 0) return CGB_OK;
+    if (!params || !ktable || B < 0 || M <= 0 || n <= 0) return CGB_E_BADARG;
+    if (n > CGB_MAX_N || M < n || M > 256) return CGB_E_UNSUPPORTED;
+    if (nparams != van_nparams(M)) return CGB_E_UNSUPPORTED;      // nlayers 2, modelsize 16, nheads 4, nhidden 32 only
+    VanParams p;
+    p.params = params; p.ktable = ktable; p.M = M; p.n = n; p.B = B; p.state_in = state_in; p.gumbel = gumbel;
+    p.seed = seed; p.out_state = out_state; p.out_logprob = out_logprob; p.out_logits = out_logits;
+    return launch_van(p, (cudaStream_t)stream);
+}
+
+int cgb_van_sample_f64io(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n, int B,
+                         const double* gumbel, uint64_t seed, int32_t* out_state_idx, double* out_logprob,
+                         double* out_logits) {
+    if (B != 0 && !out_state_idx) return CGB_E_BADARG;
+    return run_van(stream, params, nparams, ktable, M, n, B, nullptr, gumbel, seed, out_state_idx, out_logprob, out_logits);
+}
+
+int cgb_van_logprob_f64io(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n, int B,
+                          const int32_t* state_idx, double* out_logprob, double* out_logits) {
+    if (B != 0 && (!state_idx || !out_logprob)) return CGB_E_BADARG;
+    return run_van(stream, params, nparams, ktable, M, n, B, state_idx, nullptr, 0, nullptr, out_logprob, out_logits);
+}
+
 int cgb_microbench(void* stream, int kind, int blocks, int iters, float* out) {
     if (kind < 0 || kind > 2 || blocks <= 0 || iters <= 0 || !out) return CGB_E_BADARG;
     return launch_microbench(kind, blocks, iters, out, (cudaStream_t)stream);

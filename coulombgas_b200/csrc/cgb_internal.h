@@ -85,4 +85,17 @@ struct EwaldParams {
 int launch_ewald(const EwaldParams& p, cudaStream_t st);
 int launch_microbench(int kind, int blocks, int iters, float* out, cudaStream_t st);
 
+// autoregressive momentum sampler (cgb_van.cu)
+struct VanParams {
+    const double* params; const double* ktable; int M, n, B;
+    const int32_t* state_in;      // (B,n) or null: given choices (log_prob mode)
+    const double* gumbel;         // (B,n,M) or null
+    uint64_t seed;
+    int32_t* out_state;           // (B,n) or null
+    double* out_logprob;          // (B) or null
+    double* out_logits;           // (B,n,M) masked logits, or null
+};
+size_t van_nparams(int M);
+int launch_van(const VanParams& p, cudaStream_t st);
+
 }  // namespace cgb

@@ -107,6 +107,25 @@ int cgb_mcmc_sweep_f64io(void* stream, double* x_inout, const int32_t* state_idx
 int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, double rs, double kappa,
                     const float* items, int n_items, int gmax, double* out_V);
 
+/* ---- autoregressive momentum sampler (SURVEY section 8 f/N2: the caller right before the sweep) -------------- */
+/* Replaces `sampler(params_van, key, batch)` and `log_prob(params_van, state_idx)` of
+ * make_autoregressive_sampler (src/sampler.py:30-44) for the causal Transformer of src/autoregressive.py:50-96
+ * with the reference's default shape (main.py:24-27: nlayers 2, modelsize 16, nheads 4, nhidden 32; input = the
+ * 2 components of the occupied k vector).  params: flat float64 device vector of cgb_van_nparams(M) = 18 M + 4368
+ * entries in the order  x1hat[M] | embedding_mlp w[2][16] b[16] | per layer {query, key, value, linear: w[16][16]
+ * b[16]; mlp/linear w[16][32] b[32]; mlp/linear_1 w[32][16] b[16]} | output_mlp w[16][M] b[M]   (haiku [in][out]).
+ * ktable (M,2) f64 device = sp_indices_twist.  n <= 64, n <= M <= 256.
+ * sample: gumbel (B,n,M) f64 = the Gumbel noise jax.random.categorical would add to the logits (parity mode), or
+ *   NULL -> Philox4x32-10 keyed by (seed; walker, draw, orbital).  out_state_idx (B,n) int32 strictly increasing;
+ *   out_logprob (B) f64 = log_prob of the drawn states, or NULL; out_logits (B,n,M) f64 masked logits, or NULL.
+ * logprob: the same pass with the choices given (sampler.py:40-44). */
+size_t cgb_van_nparams(int M);
+int cgb_van_sample_f64io(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n,
+                         int B, const double* gumbel, uint64_t seed, int32_t* out_state_idx, double* out_logprob,
+                         double* out_logits);
+int cgb_van_logprob_f64io(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n,
+                          int B, const int32_t* state_idx, double* out_logprob, double* out_logits);
+
 /* ---- roofline micro-benchmarks (bench.py only): FFMA / MUFU.EX2 saturating kernels ---------- */
 /* Runs `iters` dependent-chain iterations on `blocks` x 256 threads; writes a checksum to out (1 float).
  * kind 0: 8 independent FFMA chains per thread (2*8*iters flop per thread);
