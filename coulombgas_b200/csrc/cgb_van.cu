@@ -23,6 +23,7 @@ namespace cgb {
 
 namespace van {
 constexpr int D = 16, H = 4, KS = 4, HID = 32, NL = 2;
+constexpr int KVP = 33;                                // KV-cache row pitch (doubles): odd, so the per-position score loads of 32 lanes spread over all banks
 // flat parameter layout (doubles), M = number of orbitals:  x1hat[M] | emb w[2][16] b[16] |
 //   per layer: q w[16][16] b[16] | k .. | v .. | o .. | mlp1 w[16][32] b[32] | mlp2 w[32][16] b[16] |  out w[16][M] b[M]
 constexpr int LIN = D * D + D;                         // 272
@@ -53,10 +54,10 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
     for (int t = threadIdx.x; t < np; t += blockDim.x) sP[t] = p.params[t];
     __syncthreads();
     const int np_pad = (np + 1) & ~1;
-    // per-warp slice: KV cache [NL][n][32] (keys 0..15, values 16..31), scratch x[16] q[16] att[16] hid[32] y[16], wts[H][64]
-    const int slice = NL * n * 32 + 96 + H * 64;
+    // per-warp slice: KV cache [NL][n][KVP] (keys 0..15, values 16..31), scratch x[16] q[16] att[16] hid[32] y[16], wts[H][64]
+    const int slice = NL * n * KVP + 96 + H * 64;
     double* const sKV = sP + np_pad + (size_t)warp * slice;
-    double* const sx = sKV + NL * n * 32;
+    double* const sx = sKV + NL * n * KVP;
     double* const sq = sx + 16;
     double* const satt = sq + 16;
     double* const shid = satt + 16;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
 #pragma unroll 1
                 for (int l = 0; l < NL; ++l) {
                     const double* Wl = sP + o_layer(M, l);
-                    double* kv = sKV + ((size_t)l * n + t) * 32;
+                    double* kv = sKV + ((size_t)l * n + t) * KVP;
                     {   // lanes 0..15: query then value; lanes 16..31: key
                         const double* Wa = Wl + (lane < 16 ? 0 : LIN);
                         double a = Wa[D * D + c], v = Wl[2 * LIN + D * D + c];
@@ -98,11 +99,11 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                     for (int h = 0; h < H; ++h) {
                         double s0 = -INFINITY, s1 = -INFINITY;
                         if (lane <= t) {
-                            const double* kk = sKV + ((size_t)l * n + lane) * 32 + KS * h;
+                            const double* kk = sKV + ((size_t)l * n + lane) * KVP + KS * h;
                             s0 = 0.5 * (sq[KS * h] * kk[0] + sq[KS * h + 1] * kk[1] + sq[KS * h + 2] * kk[2] + sq[KS * h + 3] * kk[3]);
                         }
                         if (lane + 32 <= t) {
-                            const double* kk = sKV + ((size_t)l * n + lane + 32) * 32 + KS * h;
+                            const double* kk = sKV + ((size_t)l * n + lane + 32) * KVP + KS * h;
                             s1 = 0.5 * (sq[KS * h] * kk[0] + sq[KS * h + 1] * kk[1] + sq[KS * h + 2] * kk[2] + sq[KS * h + 3] * kk[3]);
                         }
                         const double mx = warp_max_f64(fmax(s0, s1));
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                     if (lane < 16) {
                         double a = 0.0;
                         const double* wv = swt + (c >> 2) * 64;
-                        for (int tau = 0; tau <= t; ++tau) a = fma(wv[tau], sKV[((size_t)l * n + tau) * 32 + 16 + c], a);
+                        for (int tau = 0; tau <= t; ++tau) a = fma(wv[tau], sKV[((size_t)l * n + tau) * KVP + 16 + c], a);
                         satt[c] = a;
                     }
                     __syncwarp();
@@ -217,7 +218,7 @@ int launch_van(const VanParams& p, cudaStream_t st) {
     using namespace van;
     if (p.M < p.n || p.M > 256 || p.n < 1 || p.n > 64) return CGB_E_UNSUPPORTED;
     const size_t np_pad = (nparams(p.M) + 1) & ~size_t(1);
-    const size_t slice = (size_t)NL * p.n * 32 + 96 + H * 64;
+    const size_t slice = (size_t)NL * p.n * KVP + 96 + H * 64;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
