@@ -37,29 +37,36 @@ def _lattice(dim, nmax):
     return np.stack([m.reshape(-1) for m in mesh], axis=1)
 
 
-def sp_orbitals(dim, Emax=60):
-    """src/orbitals.py:22-44 -> (indices (M, dim) int, Es (M,) int), ascending |m|^2 <= Emax."""
+def sp_orbitals(dim, Emax=60, kind=None):
+    """src/orbitals.py:22-44 -> (indices (M, dim) int, Es (M,) int), ascending |m|^2 <= Emax.
+
+    CAVEAT: the reference orders DEGENERATE orbitals by numpy's default argsort, which is unstable and has
+    changed between NumPy versions / CPU dispatch paths.  `kind=None` reproduces "whatever this NumPy does", like the
+    reference; pass kind="stable" for a platform-independent table.  Parameters trained by the reference (the VAN in
+    particular) are tied to the order of the NumPy they were trained with — keep the k-table of a run next to its
+    checkpoints instead of regenerating it (tests/golden/van_n13_pretrained.npz carries the recovered order of the
+    shipped Emax=25 runs)."""
     lat = _lattice(dim, int(np.floor(np.sqrt(Emax))))
     e = np.sum(lat * lat, axis=1)
     sel = e <= Emax
     lat, e = lat[sel], e[sel]
-    perm = e.argsort()          # numpy default kind, as the reference: tie order must be reproduced, not improved
+    perm = e.argsort(kind=kind)  # numpy default kind, as the reference: tie order must be reproduced, not improved
     return lat[perm], e[perm]
 
 
-def twist_sort(indices, twist):
-    """src/orbitals.py:46-55 -> (indices + twist re-sorted by twisted energy, twisted energies)."""
+def twist_sort(indices, twist, kind=None):
+    """src/orbitals.py:46-55 -> (indices + twist re-sorted by twisted energy, twisted energies).  `kind`: see sp_orbitals."""
     kt = np.asarray(indices) + np.asarray(twist, dtype=np.float64)
     e = np.sum(kt * kt, axis=1)
-    perm = e.argsort()
+    perm = e.argsort(kind=kind)
     return kt[perm], e[perm]
 
 
-def sp_indices_twist(dim, Emax, twist):
+def sp_indices_twist(dim, Emax, twist, kind=None):
     """main.py:79-90: the (M, dim) float64 k-table the kernels take as `ktable`, DESCENDING twisted energy
     (row M-1 is the lowest orbital; the ground state occupies rows M-n..M-1, main.py:101)."""
-    idx, _ = sp_orbitals(dim, Emax)
-    kt, e = twist_sort(idx, twist)
+    idx, _ = sp_orbitals(dim, Emax, kind)
+    kt, e = twist_sort(idx, twist, kind)
     return np.ascontiguousarray(kt[::-1], dtype=np.float64), np.ascontiguousarray(e[::-1], dtype=np.float64)
 
 
