@@ -362,8 +362,10 @@ def test_replay_checkpoint_tool(cg, cases, tmp_path):
     f["batch"] = B
     run = interop.run_dirname(str(tmp_path) + "/", nlayers=2, modelsize=16, nheads=4, nhidden=32, hutchinson=True, **f)
     os.makedirs(run)
+    from test_van import load_van
     interop.save_data({"keys": np.zeros((8, 2), np.uint32), "x": c["x"][:B].reshape(8, B // 8, c["n"], 2),
-                       "params_van": {}, "params_flow": c["params"], "opt_state": ()}, interop.ckpt_filename(3000, run))
+                       "params_van": load_van("n29_rs1")["params"], "params_flow": c["params"], "opt_state": ()},
+                      interop.ckpt_filename(3000, run))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "replay_checkpoint.py"), run, "--acc-steps", "2"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -371,6 +373,7 @@ def test_replay_checkpoint_tool(cg, cases, tmp_path):
     (tmp_path / "data.txt").write_text(line + "\n")
     d = interop.read_data_txt(str(tmp_path / "data.txt"))
     assert int(d["epoch"][0]) == 3000 and np.isnan(d["K"][0])
-    # ground-state occupations instead of VAN samples: same acceptance to a few percent, V within the error bars
+    assert abs(d["S"][0] - 10.079675) < 5 * np.hypot(d["S_std"][0], 0.037649) + 0.1, line      # entropy column of the shipped log
+    # occupations drawn from the checkpoint's VAN: acceptance to a few percent, V within the error bars
     assert abs(d["accept_rate"][0] - pins["accept_rate"]) < 0.08, (line, pins)
     assert abs(d["V"][0] - pins["V"]) < 5 * np.hypot(d["V_std"][0], pins["V_std"]) + 0.02 * abs(pins["V"]), (line, pins)
