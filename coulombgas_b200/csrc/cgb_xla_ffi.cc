@@ -80,4 +80,33 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(CgbEwald, EwaldImpl,
         .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F32>>()
         .Attr<double>("L").Attr<double>("rs").Attr<double>("kappa").Attr<int64_t>("gmax")
         .Ret<ffi::Buffer<ffi::F64>>());
+
+// sampler(params_van, key, batch) / log_prob(params_van, state_idx)  — replace src/sampler.py:30-44 over the Transformer of
+// src/autoregressive.py:50-96 (SURVEY section 8 f/N2).  params = the flat vector of cgb200.h (18 M + 4368 doubles).
+static ffi::Error VanSampleImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> params, ffi::Buffer<ffi::F64> ktable, int64_t n,
+                                int64_t seed_hi, int64_t seed_lo, ffi::ResultBuffer<ffi::S32> state_idx,
+                                ffi::ResultBuffer<ffi::F64> logprob) {
+    const auto d = state_idx->dimensions();              // (B, n)
+    const uint64_t seed = ((uint64_t)(uint32_t)seed_hi << 32) | (uint32_t)seed_lo;
+    return rc_to_error(cgb_van_sample_f64io(stream, params.typed_data(), params.element_count(), ktable.typed_data(),
+                                            (int)ktable.dimensions()[0], (int)n, (int)d[0], nullptr, seed,
+                                            state_idx->typed_data(), logprob->typed_data(), nullptr), "cgb_van_sample_f64io");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CgbVanSample, VanSampleImpl,
+    ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
+        .Attr<int64_t>("n").Attr<int64_t>("seed_hi").Attr<int64_t>("seed_lo")
+        .Ret<ffi::Buffer<ffi::S32>>().Ret<ffi::Buffer<ffi::F64>>());
+
+static ffi::Error VanLogProbImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> params, ffi::Buffer<ffi::F64> ktable,
+                                 ffi::Buffer<ffi::S32> state_idx, ffi::ResultBuffer<ffi::F64> logprob) {
+    const auto d = state_idx.dimensions();
+    return rc_to_error(cgb_van_logprob_f64io(stream, params.typed_data(), params.element_count(), ktable.typed_data(),
+                                             (int)ktable.dimensions()[0], (int)d[1], (int)d[0], state_idx.typed_data(),
+                                             logprob->typed_data(), nullptr), "cgb_van_logprob_f64io");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CgbVanLogProb, VanLogProbImpl,
+    ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::S32>>()
+        .Ret<ffi::Buffer<ffi::F64>>());
 #endif  // CGB_HAVE_XLA_FFI

@@ -11,6 +11,8 @@
  *   cgb_mcmc_sweep_f64io   <->  mcmc(logp_fn, x_init, key, mc_steps, mc_stddev)   src/MCMC.py:6-40
  *                               and the wrap x -= L*floor(x/L)                     src/VMC.py:24
  *   cgb_ewald_f64io        <->  potential_energy(x, kappa, G, L, rs)       src/potential.py:36-77
+ *   cgb_van_sample_f64io   <->  sampler(params_van, key, batch)            src/sampler.py:30-38   (next row N2:
+ *   cgb_van_logprob_f64io  <->  log_prob(params_van, state_idx)           src/sampler.py:40-44    the caller before the sweep)
  *
  * Conventions (all launchers):
  *   - asynchronous on the caller's stream (`stream` is a cudaStream_t passed as void*), device pointers
