@@ -119,7 +119,7 @@ def test_kernel_matches_reference_run(cg, tag):
 def test_kernel_general_shapes_vs_oracle(cg):
     rng = np.random.default_rng(2)
     from coulombgas_b200 import interop
-    for n, Emax in ((1, 4), (2, 4), (7, 9), (33, 25), (64, 49)):
+    for n, Emax in ((1, 4), (2, 4), (7, 9), (33, 25), (64, 49), (5, 81)):       # M = 13 ... 253 (limit 256)
         kt, _ = interop.sp_indices_twist(2, Emax, (0.25, 0.25))
         M = kt.shape[0]
         p = rand_params(rng, M)
@@ -134,7 +134,13 @@ def test_kernel_general_shapes_vs_oracle(cg):
         sampler(p, cg.ExplicitGumbel(g[:, :, :5]), B)
     with pytest.raises(ValueError):
         log_prob(np.zeros(10), s)
-    assert sampler(p, 3, 0).shape == (0, 64)
+    assert sampler(p, 3, 0).shape == (0, 5)
+    kt_big, _ = interop.sp_indices_twist(2, 100, (0.25, 0.25))                # M = 317 > 256: unsupported shape, loud error
+    big, _ = cg.make_autoregressive_sampler(kt_big, 5, kt_big.shape[0])
+    with pytest.raises(cg.CgbError):
+        big(rand_params(rng, kt_big.shape[0]), 1, 2)
+    with pytest.raises(NotImplementedError):
+        cg.make_autoregressive_sampler(kt, 5, M, nlayers=3)
 
 
 @gpu
