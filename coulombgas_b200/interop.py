@@ -62,12 +62,32 @@ def twist_sort(indices, twist, kind=None):
     return kt[perm], e[perm]
 
 
-def sp_indices_twist(dim, Emax, twist, kind=None):
+def sp_indices_twist(dim, Emax, twist, kind=None, order=None):
     """main.py:79-90: the (M, dim) float64 k-table the kernels take as `ktable`, DESCENDING twisted energy
-    (row M-1 is the lowest orbital; the ground state occupies rows M-n..M-1, main.py:101)."""
+    (row M-1 is the lowest orbital; the ground state occupies rows M-n..M-1, main.py:101).
+
+    order="shipped": the table with the order of degenerate orbitals the reference's SHIPPED runs (data/, twist
+    (1/4, 1/4), Emax 25 / 36 / 49) were trained with, recovered by tools/recover_tie_order.py from the exact free-fermion
+    answer of the shipped pretraining runs.  Use it to replay shipped checkpoints: with today's NumPy order
+    the shipped VAN parameters are off by up to 13 in log p (n = 57)."""
     idx, _ = sp_orbitals(dim, Emax, kind)
     kt, e = twist_sort(idx, twist, kind)
-    return np.ascontiguousarray(kt[::-1], dtype=np.float64), np.ascontiguousarray(e[::-1], dtype=np.float64)
+    kt, e = np.ascontiguousarray(kt[::-1], dtype=np.float64), np.ascontiguousarray(e[::-1], dtype=np.float64)
+    if order is None:
+        return kt, e
+    if order != "shipped":
+        raise ValueError("order must be None or 'shipped'")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "shipped_ktables.npz")
+    z = np.load(path)
+    key = "Emax%d" % Emax
+    if dim != 2 or key not in z.files or not np.allclose(np.asarray(twist, np.float64), z["twist"]):
+        raise ValueError("no recovered table for dim=%d Emax=%d twist=%s (shipped runs: dim 2, twist (1/4,1/4), Emax 25/36/49)"
+                         % (dim, Emax, tuple(twist)))
+    rec = np.ascontiguousarray(z[key], dtype=np.float64)
+    # same orbitals, same energies row by row: only degenerate ones are permuted
+    if rec.shape != kt.shape or not np.allclose((rec ** 2).sum(1), e) or sorted(map(tuple, rec)) != sorted(map(tuple, kt)):
+        raise RuntimeError("shipped_ktables.npz is inconsistent with sp_orbitals/twist_sort")
+    return rec, e
 
 
 def ground_state_indices(M, n):

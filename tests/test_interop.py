@@ -155,3 +155,29 @@ def test_data_txt_line_format(tmp_path):
     d = interop.read_data_txt(str(p))
     assert list(d["epoch"]) == [3000, 7] and d["V"][1] == -4.0 and d["S"][1] == 3.0 and d["F_std"][1] == 0.1
     assert abs(interop.observable_std(2.0, 5.0, 2048, 4) - np.sqrt(1.0 / 8192)) < 1e-15
+
+
+def test_shipped_tie_order_tables():
+    """interop.sp_indices_twist(order="shipped"): the k-tables with the degenerate-orbital order the shipped runs were trained
+    with (tools/recover_tie_order.py).  Same orbitals and energies as today's table row by row; on the shells the n=13 fixture
+    pins it agrees with the order recovered independently there; and the recovery report says the shipped parameters reach
+    the spread of log p their own runs logged."""
+    import json
+    path = os.path.join(os.path.dirname(interop.__file__), "data", "shipped_ktables.npz")
+    rep = json.loads(str(np.load(path)["report"]))
+    for Emax, M in ((25, 81), (36, 113), (49, 149)):
+        kt, es = interop.sp_indices_twist(2, Emax, (0.25, 0.25))
+        ks, es2 = interop.sp_indices_twist(2, Emax, (0.25, 0.25), order="shipped")
+        assert ks.shape == (M, 2) and np.array_equal(es, es2) and np.allclose((ks ** 2).sum(1), es)
+        assert sorted(map(tuple, ks)) == sorted(map(tuple, kt)) and not np.array_equal(ks, kt)
+    z = np.load(os.path.join(GOLDEN, "van_n13_pretrained.npz"))
+    ks, _ = interop.sp_indices_twist(2, 25, (0.25, 0.25), order="shipped")
+    shells = list(range(66, 81))                                 # the well populated shells of the n = 13 ensemble: the n = 13 and
+                                                                 # n = 29 pretraining runs pin them independently and agree
+    assert np.array_equal(ks[shells], z["ktable_trained_order"][shells])
+    for key in ("n13", "n29", "n49"):
+        r = rep[key]
+        assert r["std_recovered"] < 1.15 * r["std_logged_run"] and r["std_today"] > 10 * r["std_recovered"], r
+    assert rep["n57"]["std_today"] > 10 * rep["n57"]["std_recovered"]
+    with pytest.raises(ValueError):
+        interop.sp_indices_twist(2, 16, (0.25, 0.25), order="shipped")

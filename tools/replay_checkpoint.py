@@ -47,7 +47,10 @@ def main():
         epoch = max(int(os.path.basename(p)[6:12]) for p in glob.glob(os.path.join(args.run_dir, "epoch_*.pkl")))
     ck = interop.load_data(interop.ckpt_filename(epoch, args.run_dir))
     n, rs, L = f["n"], f["rs"], interop.box_length(f["n"], 2)
-    ktable, _ = interop.sp_indices_twist(2, f["Emax"], f["twist"])
+    try:           # the order of degenerate orbitals the shipped runs were trained with, when it is known
+        ktable, _ = interop.sp_indices_twist(2, f["Emax"], f["twist"], order="shipped")
+    except ValueError:
+        ktable, _ = interop.sp_indices_twist(2, f["Emax"], f["twist"])
     x = torch.as_tensor(interop.shard_walkers(ck["x"], rank, world)).cuda()
     B = x.shape[0]
     van = None
