@@ -66,8 +66,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
-__device__ __forceinline__ float u32_to_unit_open(uint32_t r) {   // (0,1)
-    return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+// uniform in the OPEN interval (0,1) from the top 23 bits: (k + 1/2) 2^-23 is exact in FP32, so neither end point can be
+// produced by rounding (a 24-bit variant rounds its largest value to 1.0f: log(1) = 0 breaks -log(-log(u)))
+__device__ __forceinline__ float u32_to_unit_open(uint32_t r) {
+    return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
 }
 
 }  // namespace cgb

@@ -176,10 +176,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                         else {
                             const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)i, (uint32_t)j, 2u),
                                                            make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                            // u in (0,1) from 23 bits: (k + 1/2) 2^-23 is exact in FP32 and never rounds to 1 (a 24-bit
-                            // variant does, and -log(-log(1)) = +inf would let a masked orbital win the argmax)
-                            const float u = ((float)(rr.x >> 9) + 0.5f) * (1.0f / 8388608.0f);
-                            g = (double)(-__logf(-__logf(u)));
+                            g = (double)(-__logf(-__logf(u32_to_unit_open(rr.x))));   // u strictly inside (0,1): g finite
                         }
                         const double v = a + g;
                         if (ok && v > best) { best = v; bestj = j; } // first maximum inside the lane (j ascending); masked
