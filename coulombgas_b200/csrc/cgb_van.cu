@@ -34,6 +34,44 @@ __host__ __device__ inline int o_out(int M) { return M + 48 + NL * LSZ; }
 __host__ __device__ inline size_t nparams(int M) { return (size_t)18 * M + 4368; }
 }  // namespace van
 
+// exp(x) for x <= 0 and tanh(x) in float64 without the library's special-case handling: range reduction to |f| <= ln2/2 and
+// a degree-12 Taylor polynomial (relative error < 1e-14, far inside the 1e-10 parity budget of the log-probabilities);
+// tanh = (1 - e)/(1 + e), e = exp(-2|x|), with a Newton-refined FP32 reciprocal.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double y = fmax(x * 1.4426950408889634074, -1000.0);
+    const double kf = rint(y);
+    const double f = fma(kf, -0.69314718055994530942, x < -700.0 ? -700.0 : x);     // x - kf ln2 (kf ln2 exact to 1e-17 |kf|)
+    double p = 2.08767569878680989792e-09;                                          // 1/12!
+    p = fma(p, f, 2.50521083854417187751e-08);
+    p = fma(p, f, 2.75573192239858906526e-07);
+    p = fma(p, f, 2.75573192239858906526e-06);
+    p = fma(p, f, 2.48015873015873015873e-05);
+    p = fma(p, f, 1.98412698412698412698e-04);
+    p = fma(p, f, 1.38888888888888888889e-03);
+    p = fma(p, f, 8.33333333333333333333e-03);
+    p = fma(p, f, 4.16666666666666666667e-02);
+    p = fma(p, f, 1.66666666666666666667e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return p * __hiloint2double(((int)kf + 1023) << 20, 0);
+}
+__device__ __forceinline__ double tanh_fast(double x) {
+    const double e = exp_nonpos(-2.0 * fabs(x));
+    const double d = 1.0 + e;
+    double r = (double)rcp_approx((float)d);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return copysign((1.0 - e) * r, x);
+}
+// max over the warp of a float64 value, taken in FP32 (rounded up): only used as the softmax shift, where any common
+// value within a few ulp(FP32) of the maximum is as good as the maximum itself
+__device__ __forceinline__ double warp_shift_f64(double v) {
+    float f = __double2float_ru(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, o));
+    return (double)f;
+}
 __device__ __forceinline__ double warp_max_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -76,7 +114,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                 const int t = i - 1;
                 const double kx = __ldg(p.ktable + 2 * prev), ky = __ldg(p.ktable + 2 * prev + 1);    // sp_indices[state_idx]
                 __syncwarp();
-                if (lane < 16) sx[c] = tanh(fma(kx, W_emb[c], fma(ky, W_emb[16 + c], W_emb[32 + c])));
+                if (lane < 16) sx[c] = tanh_fast(fma(kx, W_emb[c], fma(ky, W_emb[16 + c], W_emb[32 + c])));
                 __syncwarp();
 #pragma unroll 1
                 for (int l = 0; l < NL; ++l) {
@@ -106,8 +144,8 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                             const double* kk = sKV + ((size_t)l * n + lane + 32) * KVP + KS * h;
                             s1 = 0.5 * (sq[KS * h] * kk[0] + sq[KS * h + 1] * kk[1] + sq[KS * h + 2] * kk[2] + sq[KS * h + 3] * kk[3]);
                         }
-                        const double mx = warp_max_f64(fmax(s0, s1));
-                        const double e0 = lane <= t ? exp(s0 - mx) : 0.0, e1 = lane + 32 <= t ? exp(s1 - mx) : 0.0;
+                        const double mx = warp_shift_f64(fmax(s0, s1));
+                        const double e0 = lane <= t ? exp_nonpos(s0 - mx) : 0.0, e1 = lane + 32 <= t ? exp_nonpos(s1 - mx) : 0.0;
                         const double inv = 1.0 / warp_sum_f64v(e0 + e1);
                         swt[h * 64 + lane] = e0 * inv;
                         swt[h * 64 + 32 + lane] = e1 * inv;
@@ -133,7 +171,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                         double a = W1[D * HID + lane];
 #pragma unroll
                         for (int e = 0; e < D; ++e) a = fma(sx[e], W1[e * HID + lane], a);
-                        shid[lane] = tanh(a);
+                        shid[lane] = tanh_fast(a);
                     }
                     __syncwarp();
                     if (lane < 16) {
@@ -145,7 +183,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                     }
                     __syncwarp();
                 }
-                if (lane < 16) sy[c] = tanh(sx[c]);                   // autoregressive.py:87
+                if (lane < 16) sy[c] = tanh_fast(sx[c]);                   // autoregressive.py:87
                 __syncwarp();
             }
             // ---------------- logits of draw i, mask, draw / given choice, log-softmax ----------------
@@ -193,11 +231,11 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                 idx = __reduce_min_sync(0xffffffffu, best == gbest ? bestj : 0x7fffffff);   // argmax takes the first maximum
             }
             // log-softmax of the masked logits at idx  (sampler.py:41-43)
-            lmax = warp_max_f64(lmax);
+            lmax = warp_shift_f64(lmax);
             double se = 0.0;
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-                if (lane + 32 * r < M) se += exp(lg[r] - lmax);
+                if (lane + 32 * r < M) se += exp_nonpos(lg[r] - lmax);
             se = warp_sum_f64v(se);
             const int own = idx >> 5;
             double li = 0.0;
