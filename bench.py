@@ -254,6 +254,18 @@ def main():
     except Exception:                                  # pragma: no cover
         ew_reps, ew_mode = 200, "200 back-to-back calls"
         ms_ewald = time_fn(lambda: [few() for _ in range(ew_reps)], 3) / ew_reps
+    # ---- the caller right before the sweep (SURVEY §8 f/N2): VAN draw of the occupied orbitals, reported beside the headline
+    van_info = None
+    try:
+        from test_van import load_van
+        vc = load_van("n29_rs1")
+        van = cg.VanSampler(vc["ktable"], vc["n"], vc["M"])
+        pv = torch.as_tensor(cg.pack_van_params(vc["params"]), device=dev)
+        ms_van = time_fn(lambda: van.sampler(pv, 9, B, return_log_prob=True), 5)
+        van_info = {"kernel": "van_kernel", "ms": ms_van, "walkers_per_sec": world * B / (ms_van * 1e-3),
+                    "note": "n=29 M=81 draws + log_prob for the same batch; not part of the timed step (north_star keeps the VAN outside the path)"}
+    except Exception as e:                                   # pragma: no cover
+        van_info = {"error": repr(e)}
     blocks = 148 * 8
     ffma = max(2 * 8 * 20000 * blocks * 256 / cg.microbench(0, blocks, 20000) for _ in range(3)) / 1e12
     mufu = max(8 * 20000 * blocks * 256 / cg.microbench(1, blocks, 20000) for _ in range(3)) / 1e12
@@ -325,6 +337,7 @@ def main():
                              "(MEASURED_PEAKS.json has only HBM %s GB/s and bf16); MUFU peak %.2f Top/s"
                              % (peaks.get("hbm_gbs"), mufu)},
         "wall_s_timed_region": t_wall,
+        "van_sampler": van_info,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
