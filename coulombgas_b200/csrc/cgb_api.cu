@@ -1,6 +1,7 @@
 // C ABI of libcgb200.so (include/cgb200.h): argument checking, host-side table preparation, launches.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <map>
 #include <utility>
 #include "cgb_internal.h"
@@ -112,11 +113,22 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     // Latency: when the batch cannot fill the machine with one warp per walker (B200: 148 SMs x 12 warps), the
     // CTA-per-walker kernel (cgb_sweep.cu; 4 lanes per particle) finishes a sweep sooner -- measured cross-over
     // (tools/time_small_batches.py): B ~ 700 at n = 13, B ~ 400 at n = 29.  Every other n uses the CTA kernel.
-    // CGB_SWEEP_KERNEL=cta forces the CTA kernel, =warp prefers the warp kernel wherever an instance exists.
+    // Smaller still (B <= 444: every walker gets a CTA of its own): the warp kernel's speculative mode, which spends the
+    // idle warp slots on evaluating the proposals of the next 2-3 steps at once (bit-identical trajectory).
+    // CGB_SWEEP_KERNEL=cta forces the CTA kernel, =warp prefers the warp kernel (ready queue) wherever an instance
+    // exists, =spec its speculative mode.
     const char* kk = getenv("CGB_SWEEP_KERNEL");
     bool use_warp = wsweep_supported(n) && B > (n <= 16 ? 768 : 384);
-    if (kk && kk[0] == 'c') use_warp = false;
-    if (kk && kk[0] == 'w') use_warp = wsweep_supported(n);
+    const bool spec_ok = wsweep_supported(n) && mc_steps > 0;
+    p.spec = (spec_ok && B <= wsweep_spec_capacity(n)) ? 4 : 0;          // warps per walker: 4 (two steps per round) ...
+    if (p.spec && 3 * B <= wsweep_spec_capacity(n)) p.spec = 8;          // ... or 8 (three) when B <= #SMs
+    if (kk && kk[0] == 'c') { use_warp = false; p.spec = 0; }
+    if (kk && kk[0] == 'w') { use_warp = wsweep_supported(n); p.spec = 0; }
+    if (kk && kk[0] == 's') {                                            // spec (width by batch size), spec4, spec8
+        const char d = strlen(kk) >= 5 ? kk[4] : 0;
+        p.spec = !spec_ok ? 0 : (d == '8' ? 8 : (d == '4' || !p.spec ? 4 : p.spec));
+    }
+    if (p.spec) use_warp = true;
     if (use_warp) return launch_wsweep(p, ws + WS_WCONST, st);
     int rc = launch_prep_params(params, (float*)workspace, st);
     if (rc) return rc;

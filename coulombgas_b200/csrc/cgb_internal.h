@@ -53,6 +53,7 @@ struct SweepParams {
     int* done;                    // (B) steps completed per walker
     double* ws_logp;              // (B) current log p per walker
     int* ws_nacc;                 // (B) accepted moves so far
+    int spec;                     // 4 / 8: speculative mode, warps per walker (one CTA evaluates the next 2-3 / 3-4 steps' proposals at once)
 };
 
 // workspace layout (bytes); the B-dependent arrays start at WS_DYN
@@ -76,6 +77,7 @@ int launch_prep_params(const double* params, float* wpack, cudaStream_t st);
 // warp-per-walker sweep (n <= 32, instantiated shapes only): returns CGB_E_UNSUPPORTED when n has no instance
 bool wsweep_supported(int n);
 int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st);
+int wsweep_spec_capacity(int n);
 
 struct EwaldParams {
     const double* x; int B, n; double L, rs, kappa;

@@ -124,6 +124,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+#ifndef CGBW_CTA_SYNC
+#define CGBW_CTA_SYNC 0     // 1: CTA-synchronous pops (instruction-cache sharing experiment)
+#endif
 #ifndef CGBW_KAHAN
 #define CGBW_KAHAN 1        // 0: plain FP32 partner sums (precision experiment)
 #endif
@@ -238,10 +241,21 @@ struct WShared {
     double w1c[4][16][4];
     double w0c[4][5][4];
 };
-constexpr int W_SHARED_BYTES = (sizeof(WShared) + 15) & ~15;
+constexpr int W_SHARED_BYTES = ((sizeof(WShared) + 15) & ~15) + 128;      // + the speculative mode's log p exchange slots
 
-template <int N>
-__global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
+// SPECW = 4 or 8: speculative ("prefetching") Metropolis for batches that leave most warp slots empty (SPECW = 0: the
+// ready-queue kernel).  One CTA of SPECW warps owns one walker for the whole sweep; per round the warps evaluate,
+// concurrently, the complete binary decision tree of the next D = log2(SPECW) steps -- the next proposal (node 1), BOTH
+// proposals of the step after it (node 2: first one rejected, node 3: accepted), ... -- and the last warp one node of
+// level D (all-rejected or all-accepted path, whichever the running acceptance favours; in the first round: log p of
+// the initial walker instead).  The proposal noise and the uniforms are keyed by (walker, step), so a node's
+// configuration is known before the decisions above it; after ONE block barrier every warp replays the accept/reject
+// decisions along the realised path (MCMC.py:28-33, same arithmetic, same order) and the chain advances D to D+1 steps
+// per evaluation latency.  The trajectory is bit-identical to the sequential kernel's.
+template <int N, int SPECW>
+__global__ void __launch_bounds__(SPECW == 8 ? 256 : 128, SPECW == 8 ? 1 : 3) wsweep_kernel(const SweepParams p) {
+    constexpr bool SPEC = SPECW != 0;
+    static_assert(SPECW == 0 || SPECW == 4 || SPECW == 8, "speculation tree: 4 or 8 warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using L_ = WLay<N>;
     constexpr unsigned FULL = 0xffffffffu;
@@ -291,9 +305,67 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
     const unsigned long long total = (unsigned long long)p.B * (unsigned long long)(p.mc_steps + 1);
     const unsigned long long qmask = (unsigned long long)p.qcap - 1ull;
 
+    // proposal noise of (walker b, step s) for this lane's particle and the Metropolis uniform of (b, s): inputs in
+    // parity mode, Philox streams keyed by (walker, step) otherwise -- independent of which warp asks, and when
+    auto add_noise = [&](double2& xq, const int b, const int s) {                  // MCMC.py:26
+        double nzx, nzy;
+        if (p.noise) {
+            double2 nz = make_double2(0.0, 0.0);
+            if (rv) nz = __ldg(reinterpret_cast<const double2*>(p.noise + (((size_t)(s - 1) * p.B + b) * N + lane) * 2));
+            nzx = nz.x; nzy = nz.y;
+        } else {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)s, (uint32_t)lane, 0u),
+                                          make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+            const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
+            float sn, cs;
+            sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
+            nzx = (double)(rad * cs); nzy = (double)(rad * sn);
+        }
+        xq.x += p.sigma * nzx;
+        xq.y += p.sigma * nzy;
+    };
+    auto uniform_of = [&](const int b, const int s) -> double {                    // MCMC.py:29
+        if (p.uniforms) return __ldg(p.uniforms + (size_t)(s - 1) * p.B + b);
+        const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)s, 0xffffffffu, 1u),
+                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        return ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
+    };
+
+    // speculative mode: the walker's chain state, replicated identically in the four warps of the CTA
+    int sp_b = blockIdx.x, sp_t = 0, sp_nacc = 0, sp_round = 0;
+    bool sp_load = true;
+    double2 sp_x = make_double2(0.0, 0.0);
+    double sp_logp = 0.0;
+    double* const sLp = reinterpret_cast<double*>(smem_raw + W_SHARED_BYTES - 128);    // [2][8] log p of the round's nodes
+
     for (;;) {
+        int b = 0, step = 0;
+        bool active = true;
+        double2 xv = make_double2(0.0, 0.0);
+        double logp_cur = 0.0;
+        if constexpr (SPEC) {
+            if (sp_b >= p.B) break;
+            b = sp_b;
+            if (sp_load) {
+                if (rv) sp_x = __ldcg(reinterpret_cast<const double2*>(p.x + ((size_t)b * N + lane) * 2));
+                sp_t = 0; sp_nacc = 0; sp_load = false;
+            }
+            const int w = (int)(threadIdx.x >> 5);
+            int node = w + 1;                                   // heap numbering: child of m is 2m + accepted
+            if (w == SPECW - 1) node = sp_t == 0 ? 0 : (2 * sp_nacc > sp_t ? 2 * SPECW - 1 : SPECW);
+            xv = sp_x;
+            if (node > 0) {
+                const int depth = 31 - __clz(node);
+                step = sp_t + 1 + depth;
+                active = step <= p.mc_steps;
+                if (active) {
+                    for (int j = 0; j < depth; ++j)
+                        if ((node >> (depth - 1 - j)) & 1) add_noise(xv, b, sp_t + 1 + j);     // accepted moves above this node
+                    add_noise(xv, b, step);
+                }
+            }
+        } else {
         // ---------------- pop the walker that has been ready longest ---------------------------------------
-        int b = 0;
         {
             unsigned long long idx = 0;
             if (lane == 0) idx = atomicAdd(p.qctr, 1ull);
@@ -312,13 +384,16 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
             b = __shfl_sync(FULL, b, 0);
         }
         __syncwarp();
-        const int step = p.mc_steps > 0 ? __ldcg(p.done + b) : 0;
+        step = p.mc_steps > 0 ? __ldcg(p.done + b) : 0;
 
-        // ---------------- walker state, proposal (MCMC.py:26), reduced coordinates -------------------------
-        double2 xv = make_double2(0.0, 0.0);
+        // ---------------- walker state, proposal (MCMC.py:26) ------------------------------------------------
         if (rv) xv = __ldcg(reinterpret_cast<const double2*>((step == 0 ? p.x : p.x_out) + ((size_t)b * N + lane) * 2));
-        double logp_cur = 0.0;
         if (step > 0) logp_cur = __ldcg(p.ws_logp + b);
+        if (step > 0) add_noise(xv, b, step);
+        }
+        double lp = 0.0, ldD = 0.0, aJ = 0.0;
+        if (!SPEC || active) {
+        // ---------------- reduced coordinates, occupied k rows ------------------------------------------------
         int mmax;
         {
             int2 mk = make_int2(0, 0);
@@ -330,23 +405,6 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 sK[lane] = mk;
             }
             mmax = __reduce_max_sync(FULL, max(abs(mk.x), abs(mk.y)));
-        }
-        if (step > 0) {
-            double nzx, nzy;
-            if (p.noise) {
-                double2 nz = make_double2(0.0, 0.0);
-                if (rv) nz = __ldg(reinterpret_cast<const double2*>(p.noise + (((size_t)(step - 1) * p.B + b) * N + lane) * 2));
-                nzx = nz.x; nzy = nz.y;
-            } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, (uint32_t)lane, 0u),
-                                              make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
-                float sn, cs;
-                sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
-                nzx = (double)(rad * cs); nzy = (double)(rad * sn);
-            }
-            xv.x += p.sigma * nzx;
-            xv.y += p.sigma * nzy;
         }
         double ux = xv.x * invL, uy = xv.y * invL;
         ux -= floor(ux); uy -= floor(uy);                       // features are L-periodic (flow.py:22-25)
@@ -931,25 +989,68 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
             aD = warp_sum_f64(aD);
             if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
         }
-        const double aJ = lacc_per_lane ? warp_sum_f64((double)lacc * 0.693147180559945309417)
-                                        : (double)lacc * 0.693147180559945309417;
+        aJ = lacc_per_lane ? warp_sum_f64((double)lacc * 0.693147180559945309417)
+                           : (double)lacc * 0.693147180559945309417;
+        ldD = aD - nlogL;
+        lp = 2.0 * ldD + aJ;                                 // logpsi.py:30,179
+        }   // evaluation
 
+        if constexpr (SPEC) {
+            // ---------------- exchange the nodes' log p, replay the decisions along the realised path ----------------
+            const int w = (int)(threadIdx.x >> 5);
+            double* const slot = sLp + (sp_round & 1) * 8;       // double-buffered: one block barrier per round
+            if (lane == 0) slot[w] = lp;
+            if (active && step == 0 && p.out_parts && lane == 0) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = aJ; }
+            __syncthreads();
+            const bool writer = w == 0 && lane == 0;
+            const int extra = 2 * sp_nacc > sp_t ? 2 * SPECW - 1 : SPECW;      // the same expression the round started with
+            const bool first = sp_t == 0;
+            double cur = sp_logp;
+            if (first) {
+                cur = slot[SPECW - 1];
+                if (p.out_logp_trace && writer) p.out_logp_trace[b] = cur;
+            }
+            int node = 1, adv = 0;
+            while (sp_t + adv < p.mc_steps) {
+                const int sl = node < SPECW ? node - 1 : ((!first && node == extra) ? SPECW - 1 : -1);
+                if (sl < 0) break;                               // not evaluated in this round
+                const int s = sp_t + adv + 1;
+                const double lpn = slot[sl];
+                const double u = uniform_of(b, s);
+                const double ratio = exp(lpn - cur);             // MCMC.py:28
+                const int acc = (u < ratio) ? 1 : 0;             // MCMC.py:29  (NaN -> reject)
+                if (acc) { cur = lpn; ++sp_nacc; add_noise(sp_x, b, s); }      // MCMC.py:31
+                if (writer) {
+                    if (p.out_acc_trace) p.out_acc_trace[(size_t)(s - 1) * p.B + b] = (uint8_t)acc;
+                    if (p.out_logp_trace) p.out_logp_trace[(size_t)s * p.B + b] = lpn;
+                }
+                node = 2 * node + acc;
+                ++adv;
+            }
+            sp_logp = cur;
+            sp_t += adv;
+            ++sp_round;
+            if (sp_t >= p.mc_steps) {                            // sweep of this walker finished
+                if (w == 0) {
+                    double2 xf = sp_x;
+                    if (p.wrap) { xf.x -= p.L * floor(xf.x / p.L); xf.y -= p.L * floor(xf.y / p.L); }   // VMC.py:24
+                    if (rv && p.mc_steps > 0) *reinterpret_cast<double2*>(p.x_out + ((size_t)b * N + lane) * 2) = xf;
+                    if (lane == 0) {
+                        if (p.out_logp) p.out_logp[b] = sp_logp;
+                        if (p.out_naccept) p.out_naccept[b] = sp_nacc;
+                    }
+                }
+                sp_b += gridDim.x;
+                sp_load = true;
+            }
+        } else {
         // ---------------- Metropolis accept / reject (MCMC.py:28-33), warp-uniform ------------------------------
-        const double ldD = aD - nlogL;
-        const double lp = 2.0 * ldD + aJ;                    // logpsi.py:30,179
         int acc = 1;
         if (step == 0) {
             logp_cur = lp;
             if (p.out_parts && lane == 0) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = aJ; }
         } else {
-            double u;
-            if (p.uniforms) {
-                u = __ldg(p.uniforms + (size_t)(step - 1) * p.B + b);
-            } else {
-                const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, 0xffffffffu, 1u),
-                                               make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                u = ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
-            }
+            const double u = uniform_of(b, step);
             const double ratio = exp(lp - logp_cur);         // MCMC.py:28
             acc = (u < ratio) ? 1 : 0;                       // MCMC.py:29  (NaN -> reject)
             if (acc) logp_cur = lp;
@@ -992,6 +1093,7 @@ __global__ void __launch_bounds__(128, 3) wsweep_kernel(const SweepParams p) {
                 st_release_u64(slot, ((unsigned long long)(unsigned)(t + 1ull) << 32) | (unsigned long long)(unsigned)b);
             }
         }
+        }
     }
 }
 
@@ -1004,6 +1106,21 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (p.spec) {          // speculative mode: one CTA of 8 (B <= #SMs) or 4 warps per walker, persistent over the sweep
+        auto go = [&](auto kern, const int nw) -> int {
+            const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * nw;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            int occ = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem);
+            if (occ < 1) occ = 1;
+            long long grid = (long long)sms * occ;
+            if (grid > (long long)p.B) grid = p.B;
+            kern<<<(int)grid, nw * 32, smem, st>>>(p);
+            return (int)cudaGetLastError();
+        };
+        return p.spec == 8 ? go(wsweep_kernel<N, 8>, 8) : go(wsweep_kernel<N, 4>, 4);
+    }
     // warps per CTA: 4 when the batch fills the machine, fewer for small batches so the walkers spread over all SMs
     int wpc = 4;
     while (wpc > 1 && (long long)p.B < (long long)sms * 3 * wpc) wpc >>= 1;
@@ -1011,17 +1128,26 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     long long max_grid = 1ll << 40;
     if (const char* s = getenv("CGB_W_GRID")) { const long long v = atoll(s); if (v >= 1) max_grid = v; }
     const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * wpc;
-    cudaError_t e = cudaFuncSetAttribute(wsweep_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wsweep_kernel<N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsweep_kernel<N>, wpc * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsweep_kernel<N, 0>, wpc * 32, smem);
     if (occ < 1) occ = 1;
     long long grid = (long long)sms * occ;
     const long long need = ((long long)p.B + wpc - 1) / wpc;      // never more warps than walkers
     if (grid > need) grid = need;
     if (grid > max_grid) grid = max_grid;
-    wsweep_kernel<N><<<(int)grid, wpc * 32, smem, st>>>(p);
+    wsweep_kernel<N, 0><<<(int)grid, wpc * 32, smem, st>>>(p);
     return (int)cudaGetLastError();
+}
+
+// walkers the speculative mode keeps in flight at once (one CTA each); above this the ready-queue kernel is the better use
+int wsweep_spec_capacity(int n) {
+    (void)n;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * 3;        // __launch_bounds__(128, 3): 168 registers per thread
 }
 
 int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
@@ -1039,11 +1165,13 @@ int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
     // concurrent sweeps with DIFFERENT parameters on different streams of one device must be serialised by the caller.
     e = cudaMemcpyToSymbolAsync(cW, wconst_staging, sizeof(WConst), 0, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return (int)e;
-    wqueue_init_kernel<<<(p.qcap + 255) / 256, 256, 0, st>>>(p.queue, (unsigned)p.qcap, (unsigned)p.B, p.qctr);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(p.done, 0, sizeof(int) * (size_t)p.B, st);
-    if (e != cudaSuccess) return (int)e;
+    if (!p.spec) {
+        wqueue_init_kernel<<<(p.qcap + 255) / 256, 256, 0, st>>>(p.queue, (unsigned)p.qcap, (unsigned)p.B, p.qctr);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemsetAsync(p.done, 0, sizeof(int) * (size_t)p.B, st);
+        if (e != cudaSuccess) return (int)e;
+    }
     switch (p.n) {
         case 9: return launch_wn<9>(p, st);
         case 13: return launch_wn<13>(p, st);

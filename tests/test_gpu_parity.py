@@ -23,12 +23,13 @@ def cg():
     return cg
 
 
-@pytest.fixture(autouse=True, params=["auto", "warp"])
+@pytest.fixture(autouse=True, params=["auto", "warp", "cta"])
 def sweep_kernel_choice(request, monkeypatch):
-    """Every test runs twice: with the library's own kernel choice (small test batches go to the CTA-per-walker
-    kernel) and with the warp-per-walker kernel preferred wherever it has an instance (n = 13, 29)."""
-    if request.param == "warp":
-        monkeypatch.setenv("CGB_SWEEP_KERNEL", "warp")
+    """Every test runs three times: with the library's own kernel choice (small batches of the warp-kernel shapes go to
+    its speculative mode), with the ready-queue warp-per-walker kernel preferred wherever it has an instance (n = 13,
+    29), and with the CTA-per-walker kernel forced."""
+    if request.param != "auto":
+        monkeypatch.setenv("CGB_SWEEP_KERNEL", request.param)
     else:
         monkeypatch.delenv("CGB_SWEEP_KERNEL", raising=False)
     return request.param
@@ -300,6 +301,36 @@ def test_ready_queue_any_batch_size(cg, cases, B, monkeypatch):
     assert np.abs(xw[same] - xc[same]).max() < 1e-12
     assert np.array_equal(trw["naccept"][same], trc["naccept"][same])
     assert np.abs(trw["logp"][same] - trc["logp"][same]).max() < RTOL * np.abs(trc["logp"]).max()
+
+
+@pytest.mark.parametrize("tag,B,S", [("n29_rs1", 1, 1), ("n29_rs1", 3, 2), ("n29_rs1", 37, 3), ("n29_rs1", 300, 7),
+                                     ("n29_rs1", 64, 50), ("n29_rs1", 500, 5), ("n13_rs10", 100, 11)])
+def test_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeypatch):
+    """Speculative Metropolis (one CTA of 4 / 8 warps per walker evaluates the proposals of the next 2-3 / 3-4 steps at once and replays the
+    decisions afterwards) must give exactly the chain of the sequential ready-queue kernel: same evaluation code, same
+    (walker, step)-keyed noise and uniforms -> bitwise equal proposals' log p, accept masks, final walkers.  Covers
+    sweeps shorter than the speculation depth, depths that do not divide the sweep, and more walkers than CTAs (500)."""
+    c = cases(tag)
+    reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+    rng = np.random.default_rng(11)
+    x0 = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2))
+    si = np.tile(c["state_idx"], (reps, 1))[:B]
+    logp = cg.make_logp(c["ktable"], c["L"])
+    noise, unif = rng.standard_normal((S, B, c["n"], 2)), rng.uniform(size=(S, B))
+    out = {}
+    for k in ("warp", "spec4", "spec8"):
+        monkeypatch.setenv("CGB_SWEEP_KERNEL", k)
+        out[k] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 1234, S, 0.1, return_trace=True)
+        out[k + "_explicit"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), cg.ExplicitNoise(noise, unif), S, 0.1,
+                                       return_trace=True)
+    for a, b in (("warp", "spec4"), ("warp_explicit", "spec4_explicit"), ("warp", "spec8"), ("warp_explicit", "spec8_explicit")):
+        (xa, acca, tra), (xb, accb, trb) = out[a], out[b]
+        assert np.array_equal(tra["accept"], trb["accept"])
+        assert np.array_equal(tra["logp_prop"], trb["logp_prop"])
+        assert np.array_equal(tra["logp"], trb["logp"])
+        assert np.array_equal(tra["naccept"], trb["naccept"])
+        assert np.array_equal(xa, xb)
+        assert acca == accb
 
 
 @pytest.mark.parametrize("n", [9, 21, 25])

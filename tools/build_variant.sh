@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 out=build/variants/$name; mkdir -p $out
-for f in cgb_sweep cgb_wsweep cgb_ewald cgb_api; do
+for f in cgb_sweep cgb_wsweep cgb_ewald cgb_van cgb_api; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c coulombgas_b200/csrc/$f.cu -o $out/$f.o &
 done
 wait

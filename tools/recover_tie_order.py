@@ -74,7 +74,7 @@ def exact_tables(n, Es, beta):
     return w, Z
 
 
-def recover(n, Emax, nsamp=400, seed=1, twist=(0.25, 0.25), Theta=0.15):
+def recover(n, Emax, nsamp=1000, seed=1, twist=(0.25, 0.25), Theta=0.15):
     d = glob.glob(os.path.join(REF, "data/freefermion/pretraining/n_%d_*/*/" % n))[0]
     p = interop.load_data(d + "params_van.pkl")
     last = open(d + "data.txt").read().strip().splitlines()[-1].split()
@@ -109,7 +109,7 @@ def recover(n, Emax, nsamp=400, seed=1, twist=(0.25, 0.25), Theta=0.15):
     for sweep in range(6):
         improved = False
         for g in sorted(groups, key=lambda g: -occ[g].sum()):
-            if occ[g].sum() < 12:
+            if occ[g].sum() < 0.03 * nsamp:
                 continue
             base, bp = kt[g].copy(), None
             for perm in itertools.permutations(range(len(g))):
@@ -125,7 +125,7 @@ def recover(n, Emax, nsamp=400, seed=1, twist=(0.25, 0.25), Theta=0.15):
         if not improved:
             break
     logged = float(last[2]) * np.sqrt(8192) * beta            # per-sample spread of log p the run reached
-    pinned = sorted(int(r) for g in groups if occ[g].sum() >= 12 for r in g)
+    pinned = sorted(int(r) for g in groups if occ[g].sum() >= 0.03 * nsamp for r in g)
     return kt0, kt, dict(n=n, Emax=Emax, M=M, std_today=start, std_recovered=best, std_logged_run=logged,
                          rows_changed=[int(r) for r in np.where((kt != kt0).any(1))[0]], rows_pinned=pinned)
 

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B timing of the two sweep kernels (CGB_SWEEP_KERNEL=warp|cta) over batch sizes: where the CTA-per-walker kernel
-(8 warps cooperate on one walker: low latency) beats the warp-per-walker kernel (throughput).  50-proposal sweeps."""
+"""A/B timing of the sweep kernels (CGB_SWEEP_KERNEL=warp|cta|spec) over batch sizes: where the CTA-per-walker kernel
+(4-8 warps cooperate on one walker: low latency) and the speculative mode of the warp kernel (one CTA per walker evaluates
+the next 2-3 steps' proposals at once) beat the ready-queue warp-per-walker kernel (throughput).  50-proposal sweeps."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -17,7 +18,7 @@ def timeit(fn, reps=3):
         best = min(best, a.elapsed_time(b))
     return best
 
-for tag, Bs in (("n13_rs10", (64, 128, 256, 512, 1024, 2048)), ("n29_rs1", (64, 128, 256, 512, 768, 1024, 1536, 2048))):
+for tag, Bs in (("n13_rs10", (64, 148, 256, 444, 512, 768)), ("n29_rs1", (64, 148, 200, 256, 296, 444, 512))):
     c = load_case(tag)
     logp = cg.make_logp(c["ktable"], c["L"])
     for B in Bs:
@@ -26,7 +27,8 @@ for tag, Bs in (("n13_rs10", (64, 128, 256, 512, 1024, 2048)), ("n29_rs1", (64, 
         si = torch.as_tensor(np.tile(c["state_idx"], (reps, 1))[:B], device="cuda")
         bound = logp.bind(c["params"], si)
         out = []
-        for k in ("warp", "cta"):
+        names = ("warp", "cta", "spec4", "spec8")
+        for k in names:
             os.environ["CGB_SWEEP_KERNEL"] = k
             out.append(timeit(lambda: cg.mcmc(bound, x.clone(), 3, 50, 0.1)))
-        print("%-9s B=%5d  warp %7.3f ms  cta %7.3f ms  -> %s" % (tag, B, out[0], out[1], "cta" if out[1] < out[0] else "warp"), flush=True)
+        print("%-9s B=%5d  warp %7.3f ms  cta %7.3f ms  spec4 %7.3f ms  spec8 %7.3f ms  -> %s" % (tag, B, out[0], out[1], out[2], out[3], names[int(np.argmin(out))]), flush=True)
