@@ -266,6 +266,19 @@ def main():
                     "note": "n=29 M=81 draws + log_prob for the same batch; not part of the timed step (north_star keeps the VAN outside the path)"}
     except Exception as e:                                   # pragma: no cover
         van_info = {"error": repr(e)}
+    # ---- the reference's own per-device shard of this configuration (batch 2048 over 8 GPUs = 256 walkers): latency regime,
+    # the library dispatches it to the speculative mode; reported beside the headline
+    shard_info = None
+    try:
+        Bs = max(1, B // 8)
+        xs_, sis_ = x[:Bs].clone(), si[:Bs].contiguous()
+        bound_s = logp.bind(params, sis_)
+        ms_shard = time_fn(lambda: cg.mcmc(bound_s, xs_, 78, S, CFG["mc_stddev"], wrap_L=c["L"]), 5)
+        shard_info = {"walkers": Bs, "ms": ms_shard, "walker_steps_per_sec": Bs * S / (ms_shard * 1e-3),
+                      "note": "one 50-step sweep of 256 walkers on one GPU (the reference's shard at batch 2048 / 8 devices); "
+                              "speculative Metropolis, 4 warps per walker"}
+    except Exception as e:                                   # pragma: no cover
+        shard_info = {"error": repr(e)}
     blocks = 148 * 8
     ffma = max(2 * 8 * 20000 * blocks * 256 / cg.microbench(0, blocks, 20000) for _ in range(3)) / 1e12
     mufu = max(8 * 20000 * blocks * 256 / cg.microbench(1, blocks, 20000) for _ in range(3)) / 1e12
@@ -338,6 +351,7 @@ def main():
                              % (peaks.get("hbm_gbs"), mufu)},
         "wall_s_timed_region": t_wall,
         "van_sampler": van_info,
+        "reference_shard": shard_info,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -109,26 +109,30 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
         p.ws_logp = (double*)(ws + o); o += ws_round(sizeof(double) * (size_t)B);
         p.ws_nacc = (int*)(ws + o);
     }
-    // kernel choice.  Throughput: the warp-per-walker kernel (cgb_wsweep.cu) for the instantiated n <= 32 shapes.
-    // Latency: when the batch cannot fill the machine with one warp per walker (B200: 148 SMs x 12 warps), the
-    // CTA-per-walker kernel (cgb_sweep.cu; 4 lanes per particle) finishes a sweep sooner -- measured cross-over
-    // (tools/time_small_batches.py): B ~ 700 at n = 13, B ~ 400 at n = 29.  Every other n uses the CTA kernel.
-    // Smaller still (B <= 444: every walker gets a CTA of its own): the warp kernel's speculative mode, which spends the
-    // idle warp slots on evaluating the proposals of the next 2-3 steps at once (bit-identical trajectory).
-    // CGB_SWEEP_KERNEL=cta forces the CTA kernel, =warp prefers the warp kernel (ready queue) wherever an instance
-    // exists, =spec its speculative mode.
+    // kernel choice (measured: tools/time_small_batches.py, profiles/r01_small_batches_spec.txt).
+    //  * throughput: the warp-per-walker kernel with its ready queue (cgb_wsweep.cu) for the instantiated n <= 32 shapes;
+    //  * latency: when the batch cannot fill the machine with one warp per walker (B200: 148 SMs x 12 warps) the idle
+    //    SMs are spent on SPECULATION -- the proposals of the next 2-3 steps of every chain are evaluated at once
+    //    (bit-identical trajectory): B <= 64: clusters of 8 CTAs of the CTA-per-walker kernel (cgb_sweep.cu), B <= 148:
+    //    8 warps per walker in the warp kernel, B <= 444: 4 warps per walker;
+    //  * in between (n = 13: 444 < B <= 768) and for every other n: the CTA-per-walker kernel, speculative (clusters of
+    //    8 or 4) whenever the clusters of the whole batch are resident at once (n = 57: B <= 74).
+    // CGB_SWEEP_KERNEL = cta | cta4 | cta8 (CTA kernel: sequential / cluster width), warp (ready queue), spec | spec4 | spec8.
     const char* kk = getenv("CGB_SWEEP_KERNEL");
-    bool use_warp = wsweep_supported(n) && B > (n <= 16 ? 768 : 384);
     const bool spec_ok = wsweep_supported(n) && mc_steps > 0;
-    p.spec = (spec_ok && B <= wsweep_spec_capacity(n)) ? 4 : 0;          // warps per walker: 4 (two steps per round) ...
-    if (p.spec && 3 * B <= wsweep_spec_capacity(n)) p.spec = 8;          // ... or 8 (three) when B <= #SMs
-    if (kk && kk[0] == 'c') { use_warp = false; p.spec = 0; }
+    const int sms = wsweep_spec_capacity(n) / 3;
+    bool use_warp = wsweep_supported(n) && B > (n <= 16 ? 768 : 384);
+    p.cspec = -1;
+    p.spec = 0;
+    if (spec_ok && B > 64) p.spec = B <= sms ? 8 : (B <= 3 * sms ? 4 : 0);
+    if (kk && kk[0] == 'c') { use_warp = false; p.spec = 0; p.cspec = strlen(kk) >= 4 ? atoi(kk + 3) : 0; }      // cta, cta4, cta8
     if (kk && kk[0] == 'w') { use_warp = wsweep_supported(n); p.spec = 0; }
     if (kk && kk[0] == 's') {                                            // spec (width by batch size), spec4, spec8
         const char d = strlen(kk) >= 5 ? kk[4] : 0;
         p.spec = !spec_ok ? 0 : (d == '8' ? 8 : (d == '4' || !p.spec ? 4 : p.spec));
     }
     if (p.spec) use_warp = true;
+    if (spec_ok && B <= 64 && !kk) use_warp = false;
     if (use_warp) return launch_wsweep(p, ws + WS_WCONST, st);
     int rc = launch_prep_params(params, (float*)workspace, st);
     if (rc) return rc;

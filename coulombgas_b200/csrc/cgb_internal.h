@@ -53,6 +53,7 @@ struct SweepParams {
     int* done;                    // (B) steps completed per walker
     double* ws_logp;              // (B) current log p per walker
     int* ws_nacc;                 // (B) accepted moves so far
+    int cspec;                    // CTA kernel's speculative mode: -1 = auto (widest tree that fits), 0 = off, 4/8 = CTAs per walker
     int spec;                     // 4 / 8: speculative mode, warps per walker (one CTA evaluates the next 2-3 / 3-4 steps' proposals at once)
 };
 

@@ -78,6 +78,22 @@ struct Smem {
     unsigned* redJ; unsigned* redD; double* lsum; int* flag;
 };
 
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// float64 load from the same shared-memory offset in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ double ld_dsmem_f64(const double* local, int rank) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(local), ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -133,10 +149,20 @@ __device__ __forceinline__ void store_quarter(float* dst, const float (&v)[32]) 
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int NW>
+// SPECC = 4, 8: speculative ("prefetching") Metropolis for batches that leave SMs idle (SPECC = 0: one CTA per walker,
+// step after step).  A thread-block CLUSTER of SPECC CTAs owns one walker; per round CTA r evaluates node r + 1 of the
+// binary decision tree of the next steps (node 1: the next proposal; nodes 2 / 3: the proposal of the step after it given
+// that the first one is rejected / accepted; ...), the last CTA one node of the level below (the all-rejected or the
+// all-accepted path, whichever the running acceptance favours; in the first round: the initial walker).  Noise and
+// uniforms are keyed by (walker, step), so every node's configuration is known up front.  One cluster barrier per round;
+// then thread 0 of every CTA reads the nodes' log p through distributed shared memory and replays the decisions along
+// the realised path (MCMC.py:28-33: same arithmetic, same order), every CTA applies the accepted moves to its replica of
+// the walker, and the chain has advanced log2(SPECC) (+1) steps in one evaluation latency.  Bit-identical trajectories.
+template <int NW, int SPECC>
 __global__ void __launch_bounds__(NW * 32, (NW <= 2 ? 10 : (NW <= 4 ? 5 : 2)))
 sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(SPECC == 0 || SPECC == 4 || SPECC == 8, "cluster width of the speculative mode");
     const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = tid >> 2, q = tid & 3;
     const bool rv = row < n;
@@ -170,7 +196,29 @@ sweep_kernel(const SweepParams p) {
     const float4* b14 = reinterpret_cast<const float4*>(s.wts + W_B1);
     const float* wf = s.wts + W_WF;                                        // [e*2+a]
 
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    // proposal noise of (walker b, step st) for coordinate tid (MCMC.py:26): an input in parity mode, else Philox keyed by
+    // (walker, step, particle) -- independent of who asks and when
+    auto noise_of = [&](const int b, const int st) -> double {
+        if (p.noise) return p.noise[((size_t)(st - 1) * p.B + b) * N2 + tid];
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)st, (uint32_t)(tid >> 1), 0u),
+                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
+        float sn, cs;
+        sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
+        return (double)(rad * ((tid & 1) ? sn : cs));
+    };
+    auto uniform_of = [&](const int b, const int st) -> double {                 // MCMC.py:29
+        if (p.uniforms) return p.uniforms[(size_t)(st - 1) * p.B + b];
+        const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)st, 0xffffffffu, 1u),
+                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        return ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
+    };
+    constexpr int CW = SPECC ? SPECC : 1;                    // CTAs per walker
+    const int crank = SPECC ? (int)cluster_ctarank() : 0;
+    double* const splp = reinterpret_cast<double*>(smem_raw + L_::o_red + 144);     // [2] this CTA's node log p, double-buffered
+    int sp_round = 0;
+
+    for (int b = blockIdx.x / CW; b < p.B; b += gridDim.x / CW) {
         __syncthreads();
         if (tid == 0) s.flag[1] = 0;
         if (tid < N2) s.xs[tid] = p.x[(size_t)b * N2 + tid];
@@ -183,30 +231,38 @@ sweep_kernel(const SweepParams p) {
             atomicMax(&s.flag[1], max(abs(mx), abs(my)));
         }
         double logp_cur = 0.0;   // thread 0 only
-        int nacc = 0;            // thread 0 only
+        int nacc = 0;            // thread 0 only (speculative mode: every thread)
+        int t_done = 0;          // speculative mode: steps decided so far
 
-        for (int step = 0; step <= p.mc_steps; ++step) {
+        for (int it = 0;; ++it) {
+          int step = it, node = 0, depth = 0;
+          bool active = true;
+          if constexpr (SPECC == 0) {
+              if (step > p.mc_steps) break;
+          } else {
+              if (it > 0 && t_done >= p.mc_steps) break;
+              node = crank + 1;                              // heap numbering: child of m is 2m + accepted
+              if (crank == SPECC - 1) node = t_done == 0 ? 0 : (2 * nacc > t_done ? 2 * SPECC - 1 : SPECC);
+              step = 0;
+              if (node > 0) {
+                  depth = 31 - __clz(node);
+                  step = t_done + 1 + depth;
+                  active = step <= p.mc_steps;
+              }
+          }
           bool use_pivot = p.force_pivot != 0;
+          if (active)
           for (;;) {           // at most two passes: unpivoted block LU, then (rarely) the pivoted fallback
             __syncthreads();
             if (tid == 0) s.flag[2] = 0;
             // ---------------- stage 0: proposal (MCMC.py:26) and reduced coordinates ----------------
             if (tid < N2) {
                 double xv = s.xs[tid];
-                if (step > 0) {
-                    double nz;
-                    if (p.noise) {
-                        nz = p.noise[((size_t)(step - 1) * p.B + b) * N2 + tid];
-                    } else {
-                        const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, (uint32_t)(tid >> 1), 0u),
-                                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                        const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
-                        float sn, cs;
-                        sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
-                        nz = (double)(rad * ((tid & 1) ? sn : cs));
-                    }
-                    xv += p.sigma * nz;
+                if constexpr (SPECC != 0) {
+                    for (int j = 0; j < depth; ++j)                     // accepted moves on the path above this node
+                        if ((node >> (depth - 1 - j)) & 1) xv += p.sigma * noise_of(b, t_done + 1 + j);
                 }
+                if (step > 0) xv += p.sigma * noise_of(b, step);
                 s.xp[tid] = xv;
                 double u = xv * invL;
                 u -= floor(u);                                   // features are L-periodic (flow.py:22-25)
@@ -823,25 +879,21 @@ sweep_kernel(const SweepParams p) {
           }
 
             // ---------------- Metropolis accept / reject (MCMC.py:28-33) ------------------------------
-            if (tid == 0) {
-                double ldJ = 0.0, ldD = 0.0;
+            double lp = 0.0, ldJ = 0.0, ldD = 0.0;
+            if (tid == 0 && active) {
                 if (use_pivot) { for (int w = 0; w < nJw; ++w) ldJ += s.lsum[8 + w]; } else { ldJ = s.lsum[15]; }
                 for (int w = 0; w < NW; ++w) ldD += s.lsum[w];
                 ldD -= (double)n * log(p.L);                     // D carries L^{-dim/2} per entry (slater.py:17)
-                const double lp = 2.0 * ldD + ldJ;               // logpsi.py:30,179
+                lp = 2.0 * ldD + ldJ;                            // logpsi.py:30,179
+            }
+            if constexpr (SPECC == 0) {
+            if (tid == 0) {
                 int acc = 1;
                 if (step == 0) {
                     logp_cur = lp;
                     if (p.out_parts) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = ldJ; }
                 } else {
-                    double u;
-                    if (p.uniforms) {
-                        u = p.uniforms[(size_t)(step - 1) * p.B + b];
-                    } else {
-                        const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)step, 0xffffffffu, 1u),
-                                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                        u = ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
-                    }
+                    const double u = uniform_of(b, step);
                     const double ratio = exp(lp - logp_cur);     // MCMC.py:28
                     acc = (u < ratio) ? 1 : 0;                   // MCMC.py:29  (NaN -> reject)
                     if (acc) { logp_cur = lp; ++nacc; }
@@ -852,33 +904,119 @@ sweep_kernel(const SweepParams p) {
             }
             __syncthreads();
             if (step > 0 && s.flag[0] && tid < N2) s.xs[tid] = s.xp[tid];     // MCMC.py:31
+            } else {
+            // speculative mode: publish this node's log p, one cluster barrier, replay the decisions of the realised path
+            double* const myslot = splp + (sp_round & 1);
+            if (tid == 0) {
+                *myslot = lp;
+                if (node == 0 && p.out_parts) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = ldJ; }
+            }
+            cluster_sync_all();
+            if (tid == 0) {
+                double lps[SPECC];
+#pragma unroll
+                for (int r = 0; r < SPECC; ++r) lps[r] = ld_dsmem_f64(myslot, r);
+                const bool first = t_done == 0, writer = crank == 0;
+                const int extra = 2 * nacc > t_done ? 2 * SPECC - 1 : SPECC;     // the same expression the round started with
+                if (first) {
+                    logp_cur = lps[SPECC - 1];
+                    if (p.out_logp_trace && writer) p.out_logp_trace[b] = logp_cur;
+                }
+                int nd = 1, adv = 0, mask = 0;
+                while (t_done + adv < p.mc_steps) {
+                    const int sl = nd < SPECC ? nd - 1 : ((!first && nd == extra) ? SPECC - 1 : -1);
+                    if (sl < 0) break;                           // not evaluated in this round
+                    const int st = t_done + adv + 1;
+                    double lpn = lps[0];
+#pragma unroll
+                    for (int r = 1; r < SPECC; ++r) lpn = sl == r ? lps[r] : lpn;
+                    const double u = uniform_of(b, st);
+                    const double ratio = exp(lpn - logp_cur);    // MCMC.py:28
+                    const int acc = (u < ratio) ? 1 : 0;         // MCMC.py:29  (NaN -> reject)
+                    if (acc) { logp_cur = lpn; mask |= 1 << adv; }
+                    if (writer) {
+                        if (p.out_acc_trace) p.out_acc_trace[(size_t)(st - 1) * p.B + b] = (uint8_t)acc;
+                        if (p.out_logp_trace) p.out_logp_trace[(size_t)st * p.B + b] = lpn;
+                    }
+                    nd = 2 * nd + acc;
+                    ++adv;
+                }
+                s.flag[0] = adv | (mask << 8);
+            }
+            __syncthreads();
+            {
+                const int adv = s.flag[0] & 0xff, mask = s.flag[0] >> 8;
+                if (tid < N2) {
+                    double xv = s.xs[tid];
+                    for (int j = 0; j < adv; ++j)
+                        if ((mask >> j) & 1) xv += p.sigma * noise_of(b, t_done + 1 + j);      // MCMC.py:31, in order
+                    s.xs[tid] = xv;
+                }
+                nacc += __popc(mask);
+                t_done += adv;
+            }
+            ++sp_round;
+            }
         }   // steps
 
         __syncthreads();
-        if (p.mc_steps > 0 && tid < N2) {
+        if (p.mc_steps > 0 && tid < N2 && crank == 0) {
             double xv = s.xs[tid];
             if (p.wrap) xv -= p.L * floor(xv / p.L);             // VMC.py:24
             p.x_out[(size_t)b * N2 + tid] = xv;
         }
-        if (tid == 0) {
+        if (tid == 0 && crank == 0) {
             if (p.out_logp) p.out_logp[b] = logp_cur;
             if (p.out_naccept) p.out_naccept[b] = nacc;
         }
     }
+    if constexpr (SPECC != 0) cluster_sync_all();     // no CTA leaves while a neighbour may still read its log p slots
+}
+
+template <int NW, int SPECC>
+static int launch_cluster(const SweepParams& p, cudaStream_t st, size_t smem, bool* fits) {
+    auto kern = sweep_kernel<NW, SPECC>;
+    *fits = false;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SPECC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(SPECC * p.B), 1, 1);
+    cfg.blockDim = dim3(NW * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }      // cannot tell: let the caller try a narrower tree
+    if (nclusters < p.B) return 0;                               // the whole batch must be in flight at once to pay off
+    *fits = true;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 template <int NW>
 static int launch_nw(const SweepParams& p, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes(p.n);
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // speculative mode (p.cspec: -1 = widest decision tree whose clusters are all resident at once, 0 = off, 4/8 = that width or off; a pair
+    // of CTAs -- 1.5 steps per round for twice the work -- was measured not to pay)
+    if (p.mc_steps > 0 && p.cspec != 0) {
+        bool fits = false;
+        int rc;
+        if (p.cspec == 8 || p.cspec < 0) { rc = launch_cluster<NW, 8>(p, st, smem, &fits); if (fits || rc) return rc; }
+        if (p.cspec == 4 || p.cspec < 0) { rc = launch_cluster<NW, 4>(p, st, smem, &fits); if (fits || rc) return rc; }
+    }
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<NW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<NW>, NW * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<NW, 0>, NW * 32, smem);
     if (occ < 1) occ = 1;
     int grid = p.B < sms * occ ? p.B : sms * occ;
-    sweep_kernel<NW><<<grid, NW * 32, smem, st>>>(p);
+    sweep_kernel<NW, 0><<<grid, NW * 32, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -333,6 +333,39 @@ def test_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeypatch):
         assert acca == accb
 
 
+@pytest.mark.parametrize("tag,B,S", [("n57_rs0.25", 1, 1), ("n57_rs0.25", 5, 2), ("n57_rs0.25", 64, 7), ("n49_rs0.5", 33, 5),
+                                     ("n29_rs1", 40, 50), ("n29_rs1", 200, 4), ("n13_rs10", 100, 11), ("n57_rs0.25", 400, 3)])
+def test_cluster_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeypatch):
+    """CTA-per-walker kernel, speculative mode: a thread-block cluster of 4 / 8 CTAs per walker evaluates the decision
+    tree of the next steps at once (log p exchanged through distributed shared memory, one cluster barrier per round).
+    Must give exactly the chain of the sequential CTA kernel (CGB_SWEEP_KERNEL=cta): identical accept masks and final
+    walkers; log p to float64 rounding (the two template instantiations contract a few float64 FMAs differently: 1e-13).
+    When the clusters of the whole batch are not resident at once the library falls back to the sequential kernel
+    (B = 400 at n = 57), same answer."""
+    c = cases(tag)
+    reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+    rng = np.random.default_rng(12)
+    x0 = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2))
+    si = np.tile(c["state_idx"], (reps, 1))[:B]
+    logp = cg.make_logp(c["ktable"], c["L"])
+    noise, unif = rng.standard_normal((S, B, c["n"], 2)), rng.uniform(size=(S, B))
+    out = {}
+    for k in ("cta", "cta4", "cta8"):
+        monkeypatch.setenv("CGB_SWEEP_KERNEL", k)
+        out[k] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 4321, S, 0.1, return_trace=True)
+        out[k + "_explicit"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), cg.ExplicitNoise(noise, unif), S, 0.1,
+                                       return_trace=True)
+    for k in ("cta4", "cta8"):
+        for a, b in (("cta", k), ("cta_explicit", k + "_explicit")):
+            (xa, acca, tra), (xb, accb, trb) = out[a], out[b]
+            assert np.array_equal(tra["accept"], trb["accept"]), k
+            assert np.abs(tra["logp_prop"] - trb["logp_prop"]).max() < 1e-11 * np.abs(tra["logp_prop"]).max(), k
+            assert np.abs(tra["logp"] - trb["logp"]).max() < 1e-11 * np.abs(tra["logp"]).max(), k
+            assert np.array_equal(tra["naccept"], trb["naccept"]), k
+            assert np.array_equal(xa, xb), k
+            assert acca == accb
+
+
 @pytest.mark.parametrize("n", [9, 21, 25])
 def test_other_warp_kernel_instances(cg, oracle, n, monkeypatch):
     """The warp-per-walker kernel is also instantiated for the other 2D closed shells below one warp (n = 9, 21, 25):

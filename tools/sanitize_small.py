@@ -10,10 +10,10 @@ for tag, B in (("n13_rs10", 3), ("n29_rs1", 3), ("n49_rs0.5", 2), ("n57_rs0.25",
     c = load_case(tag)
     logp = cg.make_logp(c["ktable"], c["L"])
     x, si = c["x"][:B].copy(), c["state_idx"][:B]
-    for kern in ("cta", "warp"):                  # both sweep kernels where n has a warp instance
+    for kern in ("cta", "warp", "spec4", "spec8", "cta4", "cta8"):     # both sweep kernels and their speculative modes
         os.environ["CGB_SWEEP_KERNEL"] = kern
         lp = logp(x, c["params"], si)
-        xs, acc = cg.mcmc(logp.bind(c["params"], si), x.copy(), 5, 3, 0.1)
+        xs, acc = cg.mcmc(logp.bind(c["params"], si), x.copy(), 5, 4, 0.1)
     del os.environ["CGB_SWEEP_KERNEL"]
     os.environ["CGB_FORCE_PIVOT"] = "1"
     lp2 = logp(x, c["params"], si)

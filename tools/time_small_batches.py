@@ -18,7 +18,9 @@ def timeit(fn, reps=3):
         best = min(best, a.elapsed_time(b))
     return best
 
-for tag, Bs in (("n13_rs10", (64, 148, 256, 444, 512, 768)), ("n29_rs1", (64, 148, 200, 256, 296, 444, 512))):
+KERNELS = ("warp", "spec4", "spec8", "cta", "cta4", "cta8", "auto")
+for tag, Bs in (("n13_rs10", (32, 64, 100, 148, 256, 444, 512, 768)), ("n29_rs1", (32, 64, 92, 148, 256, 444, 512)),
+                ("n49_rs0.5", (16, 32, 64, 74, 128, 512)), ("n57_rs0.25", (16, 32, 64, 74, 128, 512))):
     c = load_case(tag)
     logp = cg.make_logp(c["ktable"], c["L"])
     for B in Bs:
@@ -27,8 +29,12 @@ for tag, Bs in (("n13_rs10", (64, 148, 256, 444, 512, 768)), ("n29_rs1", (64, 14
         si = torch.as_tensor(np.tile(c["state_idx"], (reps, 1))[:B], device="cuda")
         bound = logp.bind(c["params"], si)
         out = []
-        names = ("warp", "cta", "spec4", "spec8")
+        names = [k for k in KERNELS if c["n"] <= 32 or not (k.startswith("spec") or k == "warp")]
         for k in names:
-            os.environ["CGB_SWEEP_KERNEL"] = k
+            if k == "auto":
+                os.environ.pop("CGB_SWEEP_KERNEL", None)
+            else:
+                os.environ["CGB_SWEEP_KERNEL"] = k
             out.append(timeit(lambda: cg.mcmc(bound, x.clone(), 3, 50, 0.1)))
-        print("%-9s B=%5d  warp %7.3f ms  cta %7.3f ms  spec4 %7.3f ms  spec8 %7.3f ms  -> %s" % (tag, B, out[0], out[1], out[2], out[3], names[int(np.argmin(out))]), flush=True)
+        print("%-10s B=%5d  " % (tag, B) + "  ".join("%s %6.3f" % (k, v) for k, v in zip(names, out)) +
+              "  ms -> %s" % names[int(np.argmin(out[:-1]))], flush=True)
