@@ -95,7 +95,13 @@ int cgb_logp_f64io(void* stream, const double* x, const int32_t* state_idx, cons
  * Outputs: out_logp (B) f64 final log p per walker; out_naccept (B) int32 accepted moves per walker
  * (accept_rate = sum / (mc_steps*B), MCMC.py:38-39 — the cross-device mean is the caller's psum);
  * out_accept_trace (mc_steps,B) uint8 or NULL; out_logp_trace (mc_steps+1,B) f64 proposal log p
- * (row 0 = initial) or NULL. */
+ * (row 0 = initial) or NULL.
+ * The library picks the kernel by (n, B): ready-queue warp-per-walker kernel for batches that fill the
+ * GPU; for small batches (the reference's per-device shards: 256 walkers at n=29, 64 at n=49/57) a
+ * speculative mode that evaluates the proposals of the next 2-3 steps of every chain at once on the
+ * otherwise idle SMs -- same noise/uniform streams, same decisions in the same order, so the result
+ * does not depend on the choice.  Environment override for A/B measurements only:
+ * CGB_SWEEP_KERNEL = warp | spec4 | spec8 | cta | cta4 | cta8. */
 int cgb_mcmc_sweep_f64io(void* stream, double* x_inout, const int32_t* state_idx, const double* ktable,
                          int M, const double twist[2], const double* params, const double* noise,
                          const double* uniforms, uint64_t seed, int mc_steps, double mc_stddev, double L,
