@@ -119,6 +119,17 @@ __device__ __forceinline__ float4 shfl4w(const float4 v, int src) {
 __device__ __forceinline__ double2 shfl2dw(const double2 v, int src) {
     return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
+// shared-memory loads the compiler may not move: software prefetch of the next chunk of a pivot line
+__device__ __forceinline__ float4 lds_pinned_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_pinned_d2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -126,6 +137,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 }
 #ifndef CGBW_CTA_SYNC
 #define CGBW_CTA_SYNC 1     // 1: the warps of a CTA pop the ready queue together (lock step: shared instruction-cache lines)
+#endif
+#ifndef CGBW_PIN_LDS
+#define CGBW_PIN_LDS 1      // 1: the LUs' next-chunk pivot-line loads are volatile asm (the compiler otherwise sinks them to their use)
 #endif
 #ifndef CGBW_WPC
 #define CGBW_WPC 4          // warps per CTA of the ready-queue kernel (12 / CGBW_WPC CTAs per SM)
@@ -817,6 +831,7 @@ wsweep_kernel(const SweepParams p) {
             for (int k = 0; k < N - 1; ++k) {
                 const float4* cur = line0 + (k & 1) * LP;
                 float4* nxt = line0 + ((k + 1) & 1) * LP;
+                const unsigned cur32 = (unsigned)__cvta_generic_to_shared(cur);
                 const int lim = N - 1 - k;                                    // live trailing blocks: registers 1..lim
                 const bool act = rv && lane > k;
                 const float4 a = Jr[0];
@@ -829,7 +844,12 @@ wsweep_kernel(const SweepParams p) {
                     if (j0 > lim) break;                                      // warp-uniform; at most three dead blocks of work
                     float4 nq[4];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) nq[t] = cur[j0 + 4 + t];      // next chunk ahead of its use (line is padded)
+                    for (int t = 0; t < 4; ++t)                               // next chunk ahead of its use (line is padded)
+#if CGBW_PIN_LDS
+                        nq[t] = lds_pinned_f4(cur32 + 16u * (unsigned)(j0 + 4 + t));
+#else
+                        nq[t] = cur[j0 + 4 + t];
+#endif
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const int j = j0 + t;
@@ -954,6 +974,7 @@ wsweep_kernel(const SweepParams p) {
             for (int k = 0; k < N; ++k) {
                 const double2* cur = dline0 + (k & 1) * LP;
                 double2* nxt = dline0 + ((k + 1) & 1) * LP;
+                const unsigned dcur32 = (unsigned)__cvta_generic_to_shared(cur);
                 const int lim = N - 1 - k;
                 singular |= (wk >> 5) == 0u;
                 done |= win;
@@ -967,7 +988,12 @@ wsweep_kernel(const SweepParams p) {
                     if (j0 > lim) break;
                     double2 nq[4];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) nq[t] = cur[j0 + 4 + t];
+                    for (int t = 0; t < 4; ++t)
+#if CGBW_PIN_LDS
+                        nq[t] = lds_pinned_d2(dcur32 + 16u * (unsigned)(j0 + 4 + t));
+#else
+                        nq[t] = cur[j0 + 4 + t];
+#endif
 #pragma unroll
                     for (int t = 0; t < 4; ++t)                               // independent first halves (written straight to the
                         if (j0 + t < N) {                                     // shifted slot): covers the DFMA latency
