@@ -19,7 +19,7 @@ def timeit(fn, reps=3):
     return best
 
 KERNELS = ("warp", "spec4", "spec8", "cta", "cta4", "cta8", "auto")
-for tag, Bs in (("n13_rs10", (32, 64, 100, 148, 256, 444, 512, 768)), ("n29_rs1", (32, 64, 92, 148, 256, 444, 512)),
+for tag, Bs in (("n13_rs10", (32, 64, 100, 148, 256, 444, 512, 768, 888, 1024)), ("n29_rs1", (32, 64, 92, 148, 256, 444, 512, 640, 740, 888)),
                 ("n49_rs0.5", (16, 32, 64, 74, 128, 512)), ("n57_rs0.25", (16, 32, 64, 74, 128, 512))):
     c = load_case(tag)
     logp = cg.make_logp(c["ktable"], c["L"])
