@@ -174,6 +174,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL print its version banner to STDOUT, ahead of the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B, S, n = args.batch, CFG["mc_steps"], CFG["n"]
     c, x_host, si_host = load_inputs(B, rank)
