@@ -347,7 +347,7 @@ def main():
         "gpu_launches": 4 * args.steps,      # per step: prep_wconst + wqueue_init + wsweep_kernel<29> + ewald_kernel
         "clocks": clocks,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
-                     "traffic": traffic, "kernel": "wsweep_kernel<29, 0>",
+                     "traffic": traffic, "kernel": "wsweep_kernel<29, %d>" % (0 if B > 444 else (4 if B > 148 else 8)),
                      "note": "compute-bound path (>2000 FLOP/B): achieved = (8n^3+895n^2+1760n)*(mc_steps+1)*B algorithmic "
                              "FLOP / CUDA-event kernel time; peak = FFMA-saturating micro-kernel measured in this run "
                              "(MEASURED_PEAKS.json has only HBM %s GB/s and bf16); MUFU peak %.2f Top/s"
