@@ -3,16 +3,17 @@
 // One WARP evaluates  log p = 2 log|det D| + log|det J|  (src/logpsi.py:22-31,179) of one walker: lane i owns
 // particle i, i.e. row i of the pair tensor (src/flow.py:22-26,46), block-row i of the flow Jacobian (which
 // replaces jax.jacfwd, src/logpsi.py:27-28) and row i of the Slater matrix (src/slater.py:14-17).  Consequences:
-//   * no block barrier anywhere: every exchange is a broadcast LDS from the warp's private shared-memory slice
-//     or a warp collective (REDUX / SHFL), ordered by __syncwarp; 12 independent warps per SM hide each
-//     other's latency chains (the two LU factorisations are sequential in the pivot index);
+//   * no block barrier inside an evaluation: every exchange is a broadcast LDS from the warp's private shared-memory
+//     slice or a warp collective (REDUX / SHFL), ordered by __syncwarp; 12 warps per SM hide each other's latency
+//     chains (the two LU factorisations are sequential in the pivot index).  The four warps of a CTA do START their
+//     evaluations together (they pop the ready queue as a group, two block barriers per evaluation): running in lock
+//     step they share instruction-cache lines -- the kernel is 126 KiB of SASS against a 32 KiB L1.5 instruction cache;
 //   * the weights are operands from the CONSTANT bank (FFMA/DFMA R, R, c[3][..], R): no register, no LDS;
 //   * both LU factorisations are register-resident AND rolled loops: every elimination step shifts the row one
 //     register to the left while it updates it (the FMA writes position j-1), so the active column is always
 //     register 0 and the loop body has compile-time register indices; the shrinking tail is cut by warp-uniform
-//     breaks.  Only the pivot line travels through a double-buffered shared-memory line.  The whole kernel is
-//     ~5k SASS instructions, so 12 warps in different phases still run out of the instruction cache (a fully
-//     unrolled first version, 330 kB of code, spent 47 % of its stall samples on instruction fetch).
+//     breaks.  Only the pivot line travels through a double-buffered shared-memory line.  (A fully unrolled first
+//     version, 330 kB of code, spent 47 % of its stall samples on instruction fetch.)
 //     J: unpivoted 2x2-block LU (J = I + small for any physical flow; monitored, with a partially pivoted
 //     shared-memory LU as fallback).  D: partially pivoted complex float64 LU with implicit row exchange, pivot
 //     search by one REDUX per step;
@@ -20,7 +21,9 @@
 //     multi-producer/multi-consumer ready queue in global memory: a free warp pops the walker that has been ready
 //     longest, evaluates one proposal, writes the walker state (x, log p, accept count; L2-resident) and pushes
 //     the walker back.  Every resident warp is busy until the last proposal, whatever the batch size (no wave
-//     quantisation, no head-of-line blocking).
+//     quantisation, no head-of-line blocking);
+//   * batches too small to fill the warp slots run SPECULATIVELY (template parameter SPECW, below): the warps of a CTA
+//     evaluate the proposals of the next 2-3 steps of one walker at once.
 // Precision: FP32 pair passes with Kahan-compensated partner sums, float64 single-particle stream, float64
 // Slater matrix and LU, float64 log-det sums and Metropolis test.
 #include "cgb_common.cuh"
