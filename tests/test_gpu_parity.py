@@ -279,7 +279,7 @@ def test_cta_kernel_still_matches_golden(cg, cases, tag, monkeypatch):
     assert np.abs(x - c["ref_mc_x"]).max() < 1e-12
 
 
-@pytest.mark.parametrize("B", [1, 3, 37, 300, 2500])
+@pytest.mark.parametrize("B", [1, 3, 37, 300, 1779, 2500])      # 1779 x 7 evaluations: not a multiple of the 4 tickets a CTA pops
 def test_ready_queue_any_batch_size(cg, cases, B, monkeypatch):
     """The proposal-granular ready queue of the warp kernel must give, for every batch size (fewer walkers than
     warps, non-multiples of anything, more walkers than resident warps), the same chains as the CTA kernel, which
