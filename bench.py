@@ -350,8 +350,9 @@ def main():
                      "traffic": traffic, "kernel": "wsweep_kernel<29, %d>" % (0 if B > 444 else (4 if B > 148 else 8)),
                      "note": "compute-bound path (>2000 FLOP/B): achieved = (8n^3+895n^2+1760n)*(mc_steps+1)*B algorithmic "
                              "FLOP / CUDA-event kernel time; peak = FFMA-saturating micro-kernel measured in this run "
-                             "(MEASURED_PEAKS.json has only HBM %s GB/s and bf16); MUFU peak %.2f Top/s"
-                             % (peaks.get("hbm_gbs"), mufu)},
+                             "(%s); MUFU peak %.2f Top/s"
+                             % ("MEASURED_PEAKS.json holds only HBM and bf16 peaks: %s" % json.dumps(peaks) if peaks else
+                                "MEASURED_PEAKS.json absent on this box; it holds only HBM and bf16 peaks anyway", mufu)},
         "wall_s_timed_region": t_wall,
         "van_sampler": van_info,
         "reference_shard": shard_info,
