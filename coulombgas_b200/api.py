@@ -253,6 +253,11 @@ def _all_reduce_sum(vec):
     return psum(vec)
 
 
+def _world():
+    from .dist import world
+    return world()
+
+
 def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
     """One sampling step of src/VMC.py:8-25 for THIS process's shard of walkers (one process per GPU replaces
     jax.pmap): the sweep (VMC.py:23), the wrap into [0,L) (VMC.py:24) and the cross-device mean of the accept
@@ -262,9 +267,10 @@ def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
     seed = _seed_of(key) if not isinstance(key, ExplicitNoise) else None
     x, acc = mcmc(logp.bind(params_flow, state_indices), x, key, mc_steps, mc_stddev, wrap_L=L)
     acc_t = acc if isinstance(acc, torch.Tensor) else torch.tensor(acc, dtype=torch.float64, device=_dev())
-    vec = torch.stack([acc_t, torch.ones((), dtype=torch.float64, device=acc_t.device)])
-    vec = _all_reduce_sum(vec)
-    rate = vec[0] / vec[1]                     # equal shards: mean of per-device means == global mean
+    _, w = _world()
+    rate = acc_t                               # equal shards (main.py:231-238): mean of per-device means == global mean
+    if w > 1:
+        rate = _all_reduce_sum(acc_t.reshape(1).clone())[0] / w
     new_key = key if seed is None else (seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
     return new_key, x, (rate if isinstance(acc, torch.Tensor) else float(rate))
 
@@ -430,11 +436,13 @@ def potential_energy(x, kappa, G, L, rs):
 
 
 def potential_stats(V):
-    """The V_mean / V2_mean entries of the pmean at src/VMC.py:46-53, as one all-reduce of [sum V, sum V^2, count]."""
+    """The V_mean / V2_mean entries of the pmean at src/VMC.py:46-53, as one all-reduce of this rank's [mean V, mean V^2]."""
     Vd, was_np = _to_dev(V, torch.float64)
-    vec = torch.stack([Vd.sum(), (Vd * Vd).sum(), torch.tensor(float(Vd.numel()), dtype=torch.float64, device=Vd.device)])
-    vec = _all_reduce_sum(vec)
-    mean, mean2 = vec[0] / vec[2], vec[1] / vec[2]
+    _, w = _world()
+    vec = torch.stack([Vd.mean(), (Vd * Vd).mean()])       # equal shards: pmean of the per-device means (VMC.py:46)
+    if w > 1:
+        vec = _all_reduce_sum(vec) / w
+    mean, mean2 = vec[0], vec[1]
     return (float(mean), float(mean2)) if was_np else (mean, mean2)
 
 

@@ -262,6 +262,17 @@ def test_empty_and_single_walker(cg, cases):
         cg.mcmc(lambda x: x, c["x"][:1], 0, 3, 0.1)
 
 
+def test_potential_stats_single_process(cg):
+    """V_mean / V2_mean entries of the pmean at src/VMC.py:46-53 (one process: plain means; the cross-rank mean of
+    equal-shard means is covered by tests/test_dist_gloo.py)."""
+    rng = np.random.default_rng(3)
+    V = rng.normal(-40.0, 2.0, 777)
+    m, m2 = cg.potential_stats(V)
+    assert abs(m - V.mean()) < 1e-12 * abs(V.mean()) and abs(m2 - (V * V).mean()) < 1e-12 * (V * V).mean()
+    mt, m2t = cg.potential_stats(torch.as_tensor(V, device="cuda"))
+    assert abs(float(mt) - V.mean()) < 1e-12 * abs(V.mean()) and abs(float(m2t) - (V * V).mean()) < 1e-12 * (V * V).mean()
+
+
 # ------------------------------------------------------------------ warp-per-walker kernel specifics
 @pytest.mark.parametrize("tag", ["n13_rs10", "n29_rs1"])
 def test_cta_kernel_still_matches_golden(cg, cases, tag, monkeypatch):
