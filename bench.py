@@ -174,10 +174,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL print its version banner to STDOUT, ahead of the JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the communicator is created; keep stdout for the one JSON line:
+        # file descriptor 1 points at stderr while the group is set up and the first collective runs
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     B, S, n = args.batch, CFG["mc_steps"], CFG["n"]
     c, x_host, si_host = load_inputs(B, rank)
     G = cg.kpoints(2, CFG["Gmax"])
