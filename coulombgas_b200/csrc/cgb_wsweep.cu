@@ -133,6 +133,11 @@ __device__ __forceinline__ double2 lds_pinned_d2(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
     return v;
 }
+// packed FP32 FMA of sm_100 (FFMA2: two IEEE fmas per lane and instruction; the scalar operand is broadcast by the
+// instruction itself, `R.F32`): same results as two fmaf, half the issue slots
+__device__ __forceinline__ float2 ffma2s(const float a, const float2 b, const float2 c) {
+    return __ffma2_rn(make_float2(a, a), b, c);
+}
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -639,8 +644,8 @@ wsweep_kernel(const SweepParams p) {
                         const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            S4[4 * c4 + kk][0] = fmaf(skv[kk], e4x, S4[4 * c4 + kk][0]);
-                            S4[4 * c4 + kk][1] = fmaf(skv[kk], e4y, S4[4 * c4 + kk][1]);
+                            const float2 s4 = ffma2s(skv[kk], make_float2(e4x, e4y), make_float2(S4[4 * c4 + kk][0], S4[4 * c4 + kk][1]));
+                            S4[4 * c4 + kk][0] = s4.x; S4[4 * c4 + kk][1] = s4.y;
                         }
                     }
                     sE4x += e4x; sE4y += e4y;
@@ -780,10 +785,10 @@ wsweep_kernel(const SweepParams p) {
 #pragma unroll
                     for (int c2 = 0; c2 < 8; ++c2) {
                         const float4 hv = hk[c2];
-                        j00 = fmaf(T[0][2 * c2], hv.x, fmaf(T[0][2 * c2 + 1], hv.z, j00));
-                        j01 = fmaf(T[0][2 * c2], hv.y, fmaf(T[0][2 * c2 + 1], hv.w, j01));
-                        j10 = fmaf(T[1][2 * c2], hv.x, fmaf(T[1][2 * c2 + 1], hv.z, j10));
-                        j11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, j11));
+                        const float2 ha = make_float2(hv.x, hv.y), hb = make_float2(hv.z, hv.w);
+                        const float2 jt = ffma2s(T[0][2 * c2], ha, ffma2s(T[0][2 * c2 + 1], hb, make_float2(j00, j01)));
+                        const float2 jb = ffma2s(T[1][2 * c2], ha, ffma2s(T[1][2 * c2 + 1], hb, make_float2(j10, j11)));
+                        j00 = jt.x; j01 = jt.y; j10 = jb.x; j11 = jb.y;
                     }
                     if (rv) sJ[lane * PB + k] = make_float4(j00, j01, j10, j11);
                     rs0 += j00; rs1 += j01; rs2 += j10; rs3 += j11;
@@ -859,10 +864,10 @@ wsweep_kernel(const SweepParams p) {
                         if (j < N) {
                             const float4 pv = pq[t];
                             float4 v = Jr[j];
-                            v.x = fmaf(l00, pv.x, fmaf(l01, pv.z, v.x));
-                            v.y = fmaf(l00, pv.y, fmaf(l01, pv.w, v.y));
-                            v.z = fmaf(l10, pv.x, fmaf(l11, pv.z, v.z));
-                            v.w = fmaf(l10, pv.y, fmaf(l11, pv.w, v.w));
+                            const float2 pa = make_float2(pv.x, pv.y), pb = make_float2(pv.z, pv.w);
+                            const float2 vt = ffma2s(l00, pa, ffma2s(l01, pb, make_float2(v.x, v.y)));
+                            const float2 vb = ffma2s(l10, pa, ffma2s(l11, pb, make_float2(v.z, v.w)));
+                            v = make_float4(vt.x, vt.y, vb.x, vb.y);
                             Jr[j - 1] = v;
                             if (j == 1) m = neg_inv(shfl4w(v, k + 1));        // next pivot block, inverted by every lane
                         }
