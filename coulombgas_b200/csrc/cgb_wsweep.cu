@@ -765,10 +765,10 @@ wsweep_kernel(const SweepParams p) {
                     const float e0x = alpha * f.sx, e2x = -alpha * f.cx, e4x = -e0x * i4d;
                     const float e1y = alpha * f.sy, e3y = -alpha * f.cy, e4y = -e1y * i4d;
                     const float d = f.d2 * (4.f * i4d);
-                    float j00 = fmaf(Q[0][0], e0x, fmaf(Q[0][2], e2x, Q[0][4] * e4x));
-                    float j01 = fmaf(Q[0][1], e1y, fmaf(Q[0][3], e3y, Q[0][4] * e4y));
-                    float j10 = fmaf(Q[1][0], e0x, fmaf(Q[1][2], e2x, Q[1][4] * e4x));
-                    float j11 = fmaf(Q[1][1], e1y, fmaf(Q[1][3], e3y, Q[1][4] * e4y));
+                    float2 jt = make_float2(fmaf(Q[0][0], e0x, fmaf(Q[0][2], e2x, Q[0][4] * e4x)),
+                                            fmaf(Q[0][1], e1y, fmaf(Q[0][3], e3y, Q[0][4] * e4y)));
+                    float2 jb = make_float2(fmaf(Q[1][0], e0x, fmaf(Q[1][2], e2x, Q[1][4] * e4x)),
+                                            fmaf(Q[1][1], e1y, fmaf(Q[1][3], e3y, Q[1][4] * e4y)));
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
                         const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
@@ -777,9 +777,13 @@ wsweep_kernel(const SweepParams p) {
                         // F_ik[c,:] = sigma_t * Wt^T E_ik   (Wt carries log2e; R carries ln2)
                         const float fx = sg * fmaf(cW.wt[0][c], e0x, fmaf(cW.wt[2][c], e2x, cW.wt[4][c] * e4x));
                         const float fy = sg * fmaf(cW.wt[1][c], e1y, fmaf(cW.wt[3][c], e3y, cW.wt[4][c] * e4y));
-                        j00 = fmaf(R[0][c], fx, j00); j01 = fmaf(R[0][c], fy, j01);
-                        j10 = fmaf(R[1][c], fx, j10); j11 = fmaf(R[1][c], fy, j11);
+                        // J rows += R_i[c] (fx, fy), packed over (x, y).  (Packing g = Wt^T E as well was measured slower:
+                        // the weight pairs need uniform-register loads and the compiler hoists all 16 g's, spilling.)
+                        const float2 fxy = make_float2(fx, fy);
+                        jt = ffma2s(R[0][c], fxy, jt);
+                        jb = ffma2s(R[1][c], fxy, jb);
                     }
+                    float j00 = jt.x, j01 = jt.y, j10 = jb.x, j11 = jb.y;
                     // mean-field coupling through hbar:  T_i H_k
                     const float4* hk = reinterpret_cast<const float4*>(sH + k * 32);
 #pragma unroll
