@@ -711,13 +711,15 @@ wsweep_kernel(const SweepParams p) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const int e = 4 * e4 + kk;
-                    float r0 = 0.f, r1 = 0.f, t0 = 0.f, t1 = 0.f, mm0 = cW.wf[e][0], mm1 = cW.wf[e][1];
+                    float2 r01 = make_float2(0.f, 0.f), t01 = make_float2(0.f, 0.f), mm01 = make_float2(cW.wf[e][0], cW.wf[e][1]);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        r0 = fmaf(wfs[c][0], cW.w1c[e][c], r0); r1 = fmaf(wfs[c][1], cW.w1c[e][c], r1);
-                        t0 = fmaf(wfs[c][0], cW.w1b[e][c], t0); t1 = fmaf(wfs[c][1], cW.w1b[e][c], t1);
-                        mm0 = fmaf(wfs[c][0], cW.w1a[e][c], mm0); mm1 = fmaf(wfs[c][1], cW.w1a[e][c], mm1);
+                    for (int c = 0; c < 16; ++c) {                  // packed over the two rows a = 0, 1 of WfS
+                        const float2 wv = make_float2(wfs[c][0], wfs[c][1]);
+                        r01 = ffma2s(cW.w1c[e][c], wv, r01);
+                        t01 = ffma2s(cW.w1b[e][c], wv, t01);
+                        mm01 = ffma2s(cW.w1a[e][c], wv, mm01);
                     }
+                    float r0 = r01.x, r1 = r01.y, t0 = t01.x, t1 = t01.y, mm0 = mm01.x, mm1 = mm01.y;
                     r0v[kk] = r0 * kLn2; r1v[kk] = r1 * kLn2;     // ln2: the pair pass uses Wt*log2e
                     t0v[kk] = t0; t1v[kk] = t1;
                     mm0 *= s0v[kk]; mm1 *= s0v[kk];
