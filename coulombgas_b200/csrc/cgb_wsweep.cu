@@ -204,18 +204,25 @@ __device__ __forceinline__ void softplus_sigmoid_f64w(double pre, double& sp, fl
     sg = pre >= 0.0 ? rr : ef * rr;
 }
 
-// pair features of (row i, partner j) from the half-angle table (cos, sin of pi*u): cos/sin of
-// theta = 2 pi (x_i - x_j)/L by angle addition and d^2 = sin^2(theta_x/2) + sin^2(theta_y/2)  (src/flow.py:22-25)
-struct WPairFeat { float cx, cy, sx, sy, d2; };
-__device__ __forceinline__ WPairFeat wpair_features(const float4 pi_, const float4 pj) {
-    const float shx = pi_.y * pj.x - pi_.x * pj.y, chx = fmaf(pi_.x, pj.x, pi_.y * pj.y);
-    const float shy = pi_.w * pj.z - pi_.z * pj.w, chy = fmaf(pi_.z, pj.z, pi_.w * pj.w);
+// pair features of (row i, partner j) from the half-angle table: cos/sin of theta = 2 pi (x_i - x_j)/L by angle
+// addition and d^2 = sin^2(theta_x/2) + sin^2(theta_y/2)  (src/flow.py:22-25).  Table entries are laid out
+// (cos pi u_x, cos pi u_y, sin pi u_x, sin pi u_y) so that the x and y components go through packed FP32 instructions.
+struct WHalf { float2 sh, ch; };            // sin, cos of the half-angle differences (x, y)
+__device__ __forceinline__ WHalf whalf_diff(const float4 pi_, const float2 nci, const float4 pj) {
+    const float2 ci = make_float2(pi_.x, pi_.y), si = make_float2(pi_.z, pi_.w);
+    const float2 cj = make_float2(pj.x, pj.y), sj = make_float2(pj.z, pj.w);
+    WHalf h;
+    h.sh = __ffma2_rn(si, cj, __fmul2_rn(nci, sj));          // s_i c_j - c_i s_j   (nci = -c_i)
+    h.ch = __ffma2_rn(ci, cj, __fmul2_rn(si, sj));           // c_i c_j + s_i s_j
+    return h;
+}
+struct WPairFeat { float2 c, s; float d2; };
+__device__ __forceinline__ WPairFeat wpair_features(const float4 pi_, const float2 nci, const float4 pj) {
+    const WHalf h = whalf_diff(pi_, nci, pj);
     WPairFeat f;
-    f.cx = fmaf(-2.f * shx, shx, 1.f);
-    f.cy = fmaf(-2.f * shy, shy, 1.f);
-    f.sx = 2.f * shx * chx;
-    f.sy = 2.f * shy * chy;
-    f.d2 = fmaf(shx, shx, shy * shy);
+    f.c = __ffma2_rn(__fmul2_rn(h.sh, make_float2(-2.f, -2.f)), h.sh, make_float2(1.f, 1.f));
+    f.s = __fmul2_rn(__fmul2_rn(h.sh, make_float2(2.f, 2.f)), h.ch);
+    f.d2 = fmaf(h.sh.x, h.sh.x, h.sh.y * h.sh.y);
     return f;
 }
 
@@ -447,7 +454,7 @@ wsweep_kernel(const SweepParams p) {
         }
         double ux = xv.x * invL, uy = xv.y * invL;
         ux -= floor(ux); uy -= floor(uy);                       // features are L-periodic (flow.py:22-25)
-        float4 pos;                                             // (cos, sin)(pi ux), (cos, sin)(pi uy)
+        float4 pos;                                             // (cos pi ux, cos pi uy, sin pi ux, sin pi uy)
         {
             float cs2[2], sn2[2];
 #pragma unroll 1
@@ -460,9 +467,10 @@ wsweep_kernel(const SweepParams p) {
                 const float c1 = fmaf(-pl, sn, cs), s1_ = fmaf(pl, cs, sn);
                 if (comp) { cs2[1] = c1; sn2[1] = s1_; } else { cs2[0] = c1; sn2[0] = s1_; }
             }
-            pos = make_float4(cs2[0], sn2[0], cs2[1], sn2[1]);
+            pos = make_float4(cs2[0], cs2[1], sn2[0], sn2[1]);
         }
         if (rv) sPos[lane] = pos;
+        const float2 npc = make_float2(-pos.x, -pos.y);
         __syncwarp();
 
         // ---------------- pass 1: two-particle stream, means over partners (flow.py:34-36,46) ----------------
@@ -485,15 +493,15 @@ wsweep_kernel(const SweepParams p) {
                 float4 pn = sPos[0];
 #pragma unroll 2
                 for (int k = 0; k < N; ++k) {
-                    const WPairFeat f = wpair_features(pos, pn);
+                    const WPairFeat f = wpair_features(pos, npc, pn);
                     pn = sPos[k + 1 < N ? k + 1 : k];             // next partner's table entry ahead of its use
                     const float d = sqrt_approx(f.d2);            // 0 on the diagonal (flow.py:25)
-                    m0s[0] += (double)f.cx; m0s[1] += (double)f.cy; m0s[2] += (double)f.sx; m0s[3] += (double)f.sy;
+                    m0s[0] += (double)f.c.x; m0s[1] += (double)f.c.y; m0s[2] += (double)f.s.x; m0s[3] += (double)f.s.y;
                     m0s[4] += (double)d;
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
-                                        fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], btr[c])))));
+                        const float a = fmaf(d, cW.wt[4][c], fmaf(f.s.y, cW.wt[3][c], fmaf(f.s.x, cW.wt[2][c],
+                                        fmaf(f.c.y, cW.wt[1][c], fmaf(f.c.x, cW.wt[0][c], btr[c])))));
                         sab[c] += (double)fabsf(a);
                         P[c] = fmaf(P[c], ex2_approx(-fabsf(a)), P[c]);
                     }
@@ -594,8 +602,8 @@ wsweep_kernel(const SweepParams p) {
         // i.e. O(n) work from 68 warp-wide sums (A/B per channel and direction, plus the plain sums for sum_k E_ik);
         // only the two d-feature entries (-alpha sin(th)/(4 d_ik)) need the pair loop: 32 FMA per pair instead of 96.
         {
-            const float cthx = fmaf(-2.f * pos.y, pos.y, 1.f), sthx = 2.f * pos.y * pos.x;     // full angles 2 pi u
-            const float cthy = fmaf(-2.f * pos.w, pos.w, 1.f), sthy = 2.f * pos.w * pos.z;
+            const float cthx = fmaf(-2.f * pos.z, pos.z, 1.f), sthx = 2.f * pos.z * pos.x;     // full angles 2 pi u
+            const float cthy = fmaf(-2.f * pos.w, pos.w, 1.f), sthy = 2.f * pos.w * pos.y;
             float* const sTab = sScr;                 // [N][68] contributions, then [68] sums at row 0 (h is dead: region free)
             if (rv) {
 #pragma unroll
@@ -634,17 +642,17 @@ wsweep_kernel(const SweepParams p) {
                 const float4 pj = pn;
                 pn = sPos[k + 1 < N ? k + 1 : k];
                 if (k != kself) {
-                    const float shx = pos.y * pj.x - pos.x * pj.y, chx = fmaf(pos.x, pj.x, pos.y * pj.y);
-                    const float shy = pos.w * pj.z - pos.z * pj.w, chy = fmaf(pos.z, pj.z, pos.w * pj.w);
-                    const float ai4d = (-0.5f * alpha) * rsqrt_approx(fmaf(shx, shx, shy * shy));     // -alpha / (4 d) * 2
-                    const float e4x = shx * chx * ai4d, e4y = shy * chy * ai4d;                        // -alpha sin(th)/(4 d)
+                    const WHalf hd = whalf_diff(pos, npc, pj);
+                    const float ai4d = (-0.5f * alpha) * rsqrt_approx(fmaf(hd.sh.x, hd.sh.x, hd.sh.y * hd.sh.y));     // -alpha / (4 d) * 2
+                    const float2 e4 = __fmul2_rn(__fmul2_rn(hd.sh, hd.ch), make_float2(ai4d, ai4d));                  // -alpha sin(th)/(4 d)
+                    const float e4x = e4.x, e4y = e4.y;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const float4 sk4 = *reinterpret_cast<const float4*>(sSig0 + k * 20 + 4 * c4);
                         const float skv[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const float2 s4 = ffma2s(skv[kk], make_float2(e4x, e4y), make_float2(S4[4 * c4 + kk][0], S4[4 * c4 + kk][1]));
+                            const float2 s4 = ffma2s(skv[kk], e4, make_float2(S4[4 * c4 + kk][0], S4[4 * c4 + kk][1]));
                             S4[4 * c4 + kk][0] = s4.x; S4[4 * c4 + kk][1] = s4.y;
                         }
                     }
@@ -761,11 +769,11 @@ wsweep_kernel(const SweepParams p) {
                 const float4 pj = pn;
                 pn = sPos[k + 1 < N ? k + 1 : k];
                 if (k != kself) {
-                    const WPairFeat f = wpair_features(pos, pj);
+                    const WPairFeat f = wpair_features(pos, npc, pj);
                     const float i4d = 0.25f * rsqrt_approx(f.d2);
                     // E_ik = (1/n) d t0_ik / d x_k   (5x2, 6 non-zeros)
-                    const float e0x = alpha * f.sx, e2x = -alpha * f.cx, e4x = -e0x * i4d;
-                    const float e1y = alpha * f.sy, e3y = -alpha * f.cy, e4y = -e1y * i4d;
+                    const float e0x = alpha * f.s.x, e2x = -alpha * f.c.x, e4x = -e0x * i4d;
+                    const float e1y = alpha * f.s.y, e3y = -alpha * f.c.y, e4y = -e1y * i4d;
                     const float d = f.d2 * (4.f * i4d);
                     float2 jt = make_float2(fmaf(Q[0][0], e0x, fmaf(Q[0][2], e2x, Q[0][4] * e4x)),
                                             fmaf(Q[0][1], e1y, fmaf(Q[0][3], e3y, Q[0][4] * e4y)));
@@ -773,8 +781,8 @@ wsweep_kernel(const SweepParams p) {
                                             fmaf(Q[1][1], e1y, fmaf(Q[1][3], e3y, Q[1][4] * e4y)));
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const float a = fmaf(d, cW.wt[4][c], fmaf(f.sy, cW.wt[3][c], fmaf(f.sx, cW.wt[2][c],
-                                        fmaf(f.cy, cW.wt[1][c], fmaf(f.cx, cW.wt[0][c], cW.bt[c])))));
+                        const float a = fmaf(d, cW.wt[4][c], fmaf(f.s.y, cW.wt[3][c], fmaf(f.s.x, cW.wt[2][c],
+                                        fmaf(f.c.y, cW.wt[1][c], fmaf(f.c.x, cW.wt[0][c], cW.bt[c])))));
                         const float sg = sigmoid2(a);
                         // F_ik[c,:] = sigma_t * Wt^T E_ik   (Wt carries log2e; R carries ln2)
                         const float fx = sg * fmaf(cW.wt[0][c], e0x, fmaf(cW.wt[2][c], e2x, cW.wt[4][c] * e4x));
