@@ -772,13 +772,14 @@ wsweep_kernel(const SweepParams p) {
                     const WPairFeat f = wpair_features(pos, npc, pj);
                     const float i4d = 0.25f * rsqrt_approx(f.d2);
                     // E_ik = (1/n) d t0_ik / d x_k   (5x2, 6 non-zeros)
-                    const float e0x = alpha * f.s.x, e2x = -alpha * f.c.x, e4x = -e0x * i4d;
-                    const float e1y = alpha * f.s.y, e3y = -alpha * f.c.y, e4y = -e1y * i4d;
+                    const float2 e01 = __fmul2_rn(f.s, make_float2(alpha, alpha)), e23 = __fmul2_rn(f.c, make_float2(-alpha, -alpha));
+                    const float2 e4 = __fmul2_rn(e01, make_float2(-i4d, -i4d));
+                    const float e0x = e01.x, e1y = e01.y, e2x = e23.x, e3y = e23.y, e4x = e4.x, e4y = e4.y;
                     const float d = f.d2 * (4.f * i4d);
-                    float2 jt = make_float2(fmaf(Q[0][0], e0x, fmaf(Q[0][2], e2x, Q[0][4] * e4x)),
-                                            fmaf(Q[0][1], e1y, fmaf(Q[0][3], e3y, Q[0][4] * e4y)));
-                    float2 jb = make_float2(fmaf(Q[1][0], e0x, fmaf(Q[1][2], e2x, Q[1][4] * e4x)),
-                                            fmaf(Q[1][1], e1y, fmaf(Q[1][3], e3y, Q[1][4] * e4y)));
+                    float2 jt = __ffma2_rn(make_float2(Q[0][0], Q[0][1]), e01,
+                                           __ffma2_rn(make_float2(Q[0][2], Q[0][3]), e23, __fmul2_rn(make_float2(Q[0][4], Q[0][4]), e4)));
+                    float2 jb = __ffma2_rn(make_float2(Q[1][0], Q[1][1]), e01,
+                                           __ffma2_rn(make_float2(Q[1][2], Q[1][3]), e23, __fmul2_rn(make_float2(Q[1][4], Q[1][4]), e4)));
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
                         const float a = fmaf(d, cW.wt[4][c], fmaf(f.s.y, cW.wt[3][c], fmaf(f.s.x, cW.wt[2][c],
