@@ -103,6 +103,31 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v;
 }
 
+// packed FP32 FMA of sm_100 (FFMA2: two IEEE fmas per lane and instruction, scalar operand broadcast by the instruction):
+// same results as two fmaf, half the issue slots
+__device__ __forceinline__ float2 ffma2s(const float a, const float2 b, const float2 c) {
+    return __ffma2_rn(make_float2(a, a), b, c);
+}
+
+// (a0, a1) += s * (x, y)  and  the 2x2 block update  v += L * q  of the Jacobian LU, packed where it pays: the 96-register
+// instantiations (NW <= 4) spill more with register pairs than the packed instructions save (measured: n = 13, B = 512 4 % slower)
+template <bool PK>
+__device__ __forceinline__ void pair_fma(float& a0, float& a1, const float sc, const float x, const float y) {
+    if constexpr (PK) {
+        const float2 r = ffma2s(sc, make_float2(x, y), make_float2(a0, a1));
+        a0 = r.x; a1 = r.y;
+    } else {
+        a0 = fmaf(sc, x, a0); a1 = fmaf(sc, y, a1);
+    }
+}
+template <bool PK>
+__device__ __forceinline__ void block_fma(float4& v, const float l00, const float l01, const float l10, const float l11, const float4 qv) {
+    pair_fma<PK>(v.x, v.y, l01, qv.z, qv.w);
+    pair_fma<PK>(v.x, v.y, l00, qv.x, qv.y);
+    pair_fma<PK>(v.z, v.w, l11, qv.z, qv.w);
+    pair_fma<PK>(v.z, v.w, l10, qv.x, qv.y);
+}
+
 __device__ __forceinline__ double quad_sum_f64(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -163,6 +188,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 2 ? 10 : (NW <= 4 ? 5 : 2)))
 sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(SPECC == 0 || SPECC == 4 || SPECC == 8, "cluster width of the speculative mode");
+    constexpr bool PK = NW >= 5;             // packed FP32 FMAs (FFMA2) in the 128 / 168-register instantiations
     const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = tid >> 2, q = tid & 3;
     const bool rv = row < n;
@@ -488,8 +514,8 @@ sweep_kernel(const SweepParams p) {
                                 // F_ik[c,:] = sigma_t * Wt^T E_ik   (Wt carries log2e; R carries ln2)
                                 const float fx = sg * fmaf(w0v[kk], e0x, fmaf(w2v[kk], e2x, w4v[kk] * e4x));
                                 const float fy = sg * fmaf(w1v[kk], e1y, fmaf(w3v[kk], e3y, w4v[kk] * e4y));
-                                j00 = fmaf(R[0][c], fx, j00); j01 = fmaf(R[0][c], fy, j01);
-                                j10 = fmaf(R[1][c], fx, j10); j11 = fmaf(R[1][c], fy, j11);
+                                pair_fma<PK>(j00, j01, R[0][c], fx, fy);            // J rows += R_i[c] (fx, fy)
+                                pair_fma<PK>(j10, j11, R[1][c], fx, fy);
                             }
                         }
                         if (rv) s.J[row * pB + k] = make_float4(j00, j01, j10, j11);
@@ -525,8 +551,7 @@ sweep_kernel(const SweepParams p) {
                                 // d h_k / d x_i  needs E_ki = eps . E_ik, eps = (-,-,+,+,-)
                                 const float gx = fmaf(v2v[kk], e2x, -fmaf(v0v[kk], e0x, v4v[kk] * e4x));
                                 const float gy = fmaf(v3v[kk], e3y, -fmaf(v1v[kk], e1y, v4v[kk] * e4y));
-                                Hacc[2 * c] = fmaf(skv[kk], gx, Hacc[2 * c]);
-                                Hacc[2 * c + 1] = fmaf(skv[kk], gy, Hacc[2 * c + 1]);
+                                pair_fma<PK>(Hacc[2 * c], Hacc[2 * c + 1], skv[kk], gx, gy);
                             }
                         }
                         sE[0] += e0x; sE[1] += e2x; sE[2] += e4x; sE[3] += e1y; sE[4] += e3y; sE[5] += e4y;
@@ -572,10 +597,10 @@ sweep_kernel(const SweepParams p) {
 #pragma unroll
                         for (int c2 = 0; c2 < 8; ++c2) {
                             const float4 hv = *reinterpret_cast<const float4*>(s.Hbuf + k * 36 + 4 * c2);   // (c,x),(c,y),(c+1,x),(c+1,y)
-                            t00 = fmaf(T[0][2 * c2], hv.x, fmaf(T[0][2 * c2 + 1], hv.z, t00));
-                            t01 = fmaf(T[0][2 * c2], hv.y, fmaf(T[0][2 * c2 + 1], hv.w, t01));
-                            t10 = fmaf(T[1][2 * c2], hv.x, fmaf(T[1][2 * c2 + 1], hv.z, t10));
-                            t11 = fmaf(T[1][2 * c2], hv.y, fmaf(T[1][2 * c2 + 1], hv.w, t11));
+                            pair_fma<PK>(t00, t01, T[0][2 * c2 + 1], hv.z, hv.w);
+                            pair_fma<PK>(t00, t01, T[0][2 * c2], hv.x, hv.y);
+                            pair_fma<PK>(t10, t11, T[1][2 * c2 + 1], hv.z, hv.w);
+                            pair_fma<PK>(t10, t11, T[1][2 * c2], hv.x, hv.y);
                         }
                         if (rv) {
                             float4 v = s.J[row * pB + k];
@@ -664,19 +689,13 @@ sweep_kernel(const SweepParams p) {
                                     if (m >= 1) {
                                         const float4 qv = cur[j];
                                         float4 v = Jr[m];
-                                        v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
-                                        v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
-                                        v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
-                                        v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
+                                        block_fma<PK>(v, l00, l01, l10, l11, qv);
                                         Jr[m - 1] = v;                           // shift: column 4(base+1)+q moves to slot 0
                                     }
                                 } else if (m > 0 || q > sst) {
                                     const float4 qv = cur[j];
                                     float4 v = Jr[m];
-                                    v.x = fmaf(l00, qv.x, fmaf(l01, qv.z, v.x));
-                                    v.y = fmaf(l00, qv.y, fmaf(l01, qv.w, v.y));
-                                    v.z = fmaf(l10, qv.x, fmaf(l11, qv.z, v.z));
-                                    v.w = fmaf(l10, qv.y, fmaf(l11, qv.w, v.w));
+                                    block_fma<PK>(v, l00, l01, l10, l11, qv);
                                     Jr[m] = v;
                                 }
                             }
