@@ -152,6 +152,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 #ifndef CGBW_PACK_PRE
 #define CGBW_PACK_PRE 1     // pass-1 pre-activations of channel pairs through FFMA2 (weight pairs via uniform registers): +0.9 %
 #endif
+#ifndef CGBW_PACK_PRE23
+#define CGBW_PACK_PRE23 1   // the same for the pre-activations of pass 2+3: +0.9 %
+#endif
 #ifndef CGBW_WPC
 #define CGBW_WPC 4          // warps per CTA of the ready-queue kernel (12 / CGBW_WPC CTAs per SM)
 #endif
@@ -801,8 +804,21 @@ wsweep_kernel(const SweepParams p) {
                                            __ffma2_rn(make_float2(Q[1][2], Q[1][3]), e23, __fmul2_rn(make_float2(Q[1][4], Q[1][4]), e4)));
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
+#if CGBW_PACK_PRE23
+                        float a;
+                        {
+                            const int ce = c & ~1;
+                            const float2 a2 = ffma2s(d, make_float2(cW.wt[4][ce], cW.wt[4][ce + 1]),
+                                              ffma2s(f.s.y, make_float2(cW.wt[3][ce], cW.wt[3][ce + 1]),
+                                              ffma2s(f.s.x, make_float2(cW.wt[2][ce], cW.wt[2][ce + 1]),
+                                              ffma2s(f.c.y, make_float2(cW.wt[1][ce], cW.wt[1][ce + 1]),
+                                              ffma2s(f.c.x, make_float2(cW.wt[0][ce], cW.wt[0][ce + 1]), make_float2(cW.bt[ce], cW.bt[ce + 1]))))));
+                            a = (c & 1) ? a2.y : a2.x;        // the pair is computed once: the compiler merges the two identical expressions
+                        }
+#else
                         const float a = fmaf(d, cW.wt[4][c], fmaf(f.s.y, cW.wt[3][c], fmaf(f.s.x, cW.wt[2][c],
                                         fmaf(f.c.y, cW.wt[1][c], fmaf(f.c.x, cW.wt[0][c], cW.bt[c])))));
+#endif
                         const float sg = sigmoid2(a);
                         // F_ik[c,:] = sigma_t * Wt^T E_ik   (Wt carries log2e; R carries ln2)
                         const float fx = sg * fmaf(cW.wt[0][c], e0x, fmaf(cW.wt[2][c], e2x, cW.wt[4][c] * e4x));
