@@ -13,5 +13,6 @@ device memory, streams and torch.distributed.  There is no CPU fallback.
 from ._lib import CgbError, LIB_PATH, NPARAMS  # noqa: F401
 from .api import (ExplicitNoise, Logp, BoundLogp, make_logp, mcmc, sample_x, potential_energy,  # noqa: F401
                   potential_stats, pack_params, ewald_tables, kpoints, madelung, Config, microbench,
-                  make_autoregressive_sampler, sample_stateindices_and_x, pack_van_params, ExplicitGumbel, VanSampler)
+                  make_autoregressive_sampler, sample_stateindices_and_x, pack_van_params, ExplicitGumbel, VanSampler,
+                  set_sweep_kernel, set_debug, device_key, debug_rng, SamplingStep)
 from . import flops, dist, interop  # noqa: F401

@@ -29,18 +29,20 @@ def _load():
     lib.cgb_ewald_prepare_host.argtypes = [vp, i32, f64, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.cgb_logp_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
     lib.cgb_mcmc_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
-    lib.cgb_logp_f64io.argtypes = [vp, vp, vp, vp, i32, pd2, vp, i32, i32, f64, vp, vp, vp, vp, sz]
-    lib.cgb_mcmc_sweep_f64io.argtypes = [vp, vp, vp, vp, i32, pd2, vp, vp, vp, u64, i32, f64, f64, i32, i32, i32,
-                                         vp, vp, vp, vp, vp, sz]
-    lib.cgb_ewald_f64io.argtypes = [vp, vp, i32, i32, f64, f64, f64, vp, i32, i32, vp]
+    u32 = ctypes.c_uint
+    lib.cgb_logp_f64io.argtypes = [vp, vp, vp, vp, i32, pd2, vp, i32, i32, f64, vp, vp, vp, vp, sz, u32]
+    lib.cgb_mcmc_sweep_f64io.argtypes = [vp, vp, vp, vp, i32, pd2, vp, vp, vp, u64, vp, i32, f64, f64, i32, i32, i32,
+                                         vp, vp, vp, vp, vp, vp, sz, u32]
+    lib.cgb_ewald_f64io.argtypes = [vp, vp, i32, i32, f64, f64, f64, vp, i32, i32, vp, vp]
+    lib.cgb_debug_rng.argtypes = [vp, u64, vp, i32, i32, i32, vp, vp, vp, vp, i32]
     lib.cgb_microbench.argtypes = [vp, i32, i32, i32, vp]
     lib.cgb_van_nparams.argtypes = [i32]
     lib.cgb_van_nparams.restype = sz
-    lib.cgb_van_sample_f64io.argtypes = [vp, vp, sz, vp, i32, i32, i32, vp, u64, vp, vp, vp]
+    lib.cgb_van_sample_f64io.argtypes = [vp, vp, sz, vp, i32, i32, i32, vp, u64, vp, vp, vp, vp]
     lib.cgb_van_logprob_f64io.argtypes = [vp, vp, sz, vp, i32, i32, i32, vp, vp, vp]
     for f in ("cgb_ktable_twist_host", "cgb_ewald_prepare_host", "cgb_logp_workspace_bytes",
               "cgb_mcmc_workspace_bytes", "cgb_logp_f64io", "cgb_mcmc_sweep_f64io", "cgb_ewald_f64io",
-              "cgb_microbench", "cgb_van_sample_f64io", "cgb_van_logprob_f64io"):
+              "cgb_microbench", "cgb_van_sample_f64io", "cgb_van_logprob_f64io", "cgb_debug_rng"):
         getattr(lib, f).restype = i32
     return lib
 
@@ -49,7 +51,13 @@ lib = _load()
 
 EXPORTS = ("cgb_abi_version", "cgb_error_string", "cgb_ktable_twist_host", "cgb_ewald_prepare_host",
            "cgb_logp_workspace_bytes", "cgb_mcmc_workspace_bytes", "cgb_logp_f64io", "cgb_mcmc_sweep_f64io",
-           "cgb_ewald_f64io", "cgb_microbench", "cgb_van_nparams", "cgb_van_sample_f64io", "cgb_van_logprob_f64io")
+           "cgb_ewald_f64io", "cgb_microbench", "cgb_van_nparams", "cgb_van_sample_f64io", "cgb_van_logprob_f64io",
+           "cgb_debug_rng")
+
+# per-call flags of include/cgb200.h
+KERNELS = {None: 0, "auto": 0, "cta": 1, "cta4": 2, "cta8": 3, "warp": 4, "spec4": 5, "spec8": 6, "spec": 5}
+FLAG_FORCE_PIVOT, FLAG_ADVANCE_KEY, FLAG_FORCE_F64_SLATER = 0x100, 0x200, 0x400
+STATS_LEN = 8
 
 
 def check(rc, what):

@@ -11,8 +11,46 @@ from typing import Optional
 import numpy as np
 import torch
 
+import os
+
 from . import _lib
 from ._lib import lib, check, NPARAMS
+
+# ----------------------------------------------------------------------------------------------------
+# developer switches: kernel choice / debug paths are per-call `flags` of the C ABI (include/cgb200.h).  The host layer
+# keeps a process-wide default for tests and A/B timings; the environment is read ONCE, here, at import.
+# ----------------------------------------------------------------------------------------------------
+_SWITCH = {"kernel": os.environ.get("CGB_SWEEP_KERNEL") or None, "force_pivot": os.environ.get("CGB_FORCE_PIVOT") == "1",
+           "force_f64_slater": os.environ.get("CGB_FORCE_F64_SLATER") == "1"}
+if _SWITCH["kernel"] not in _lib.KERNELS:
+    raise ValueError("CGB_SWEEP_KERNEL must be one of %s" % sorted(k for k in _lib.KERNELS if k))
+
+
+def set_sweep_kernel(name=None):
+    """Force a sweep kernel for A/B timings and tests: None/'auto', 'cta', 'cta4', 'cta8', 'warp', 'spec4', 'spec8'.
+    The results do not depend on it.  Returns the previous choice."""
+    if name not in _lib.KERNELS:
+        raise ValueError("unknown sweep kernel %r" % (name,))
+    prev, _SWITCH["kernel"] = _SWITCH["kernel"], (None if name in (None, "auto") else name)
+    return prev
+
+
+def set_debug(force_pivot=None, force_f64_slater=None):
+    """Debug paths: the partially pivoted fallback LU of the Jacobian / the float64 Slater LU for every evaluation."""
+    if force_pivot is not None:
+        _SWITCH["force_pivot"] = bool(force_pivot)
+    if force_f64_slater is not None:
+        _SWITCH["force_f64_slater"] = bool(force_f64_slater)
+
+
+def _flags(kernel=None):
+    f = _lib.KERNELS[kernel if kernel is not None else _SWITCH["kernel"]]
+    if _SWITCH["force_pivot"]:
+        f |= _lib.FLAG_FORCE_PIVOT
+    if _SWITCH["force_f64_slater"]:
+        f |= _lib.FLAG_FORCE_F64_SLATER
+    return f
+
 
 # ----------------------------------------------------------------------------------------------------
 # parameters / tables
@@ -147,7 +185,7 @@ class Logp:
         jac = torch.empty((B, 2 * n, 2 * n), dtype=torch.float32, device=xd.device) if return_jac else None
         ws = self.workspace(B, n)
         check(lib.cgb_logp_f64io(_stream(), _ptr(xd), _ptr(sd), _ptr(self.ktable_dev()), self.M, self.twist, _ptr(pd),
-                                 B, n, self.L, _ptr(out), _ptr(parts), _ptr(jac), _ptr(ws), ws.numel()),
+                                 B, n, self.L, _ptr(out), _ptr(parts), _ptr(jac), _ptr(ws), ws.numel(), _flags()),
               "cgb_logp_f64io")
         res = [out] + ([parts] if return_parts else []) + ([jac] if return_jac else [])
         if was_np:
@@ -198,44 +236,83 @@ def _seed_of(key):
     return int((k[0] << np.uint64(32)) | k[1])
 
 
-def mcmc(logp_fn, x_init, key, mc_steps, mc_stddev=0.02, wrap_L=None, return_trace=False):
+def _is_device_key(key):
+    """A CUDA tensor holding the reference's per-device PRNG key, (2,) uint32 (src/VMC.py:20): the kernels read it
+    themselves (no device->host sync, graph-capturable)."""
+    return isinstance(key, torch.Tensor) and key.is_cuda
+
+
+def _device_key(key):
+    if key.numel() != 2 or key.dtype not in (torch.uint32, torch.int32) or not key.is_contiguous():
+        raise ValueError("a device key must be a contiguous (2,) uint32 (or int32 bit pattern) CUDA tensor")
+    return key
+
+
+def device_key(seed, device=None):
+    """(2,) uint32 CUDA tensor = [seed >> 32, seed & 0xffffffff]: the device-resident form of an integer key."""
+    seed = _seed_of(seed)
+    k = np.array([seed >> 32, seed & 0xFFFFFFFF], dtype=np.uint32)
+    return torch.as_tensor(k.view(np.int32)).to(device or _dev()).view(torch.uint32)
+
+
+def mcmc(logp_fn, x_init, key, mc_steps, mc_stddev=0.02, wrap_L=None, return_trace=False, stats=None, advance_key=False,
+         _want_rate=True):
     """Metropolis sweep with the reference's signature (src/MCMC.py:7).
 
     logp_fn : a BoundLogp (`logp.bind(params_flow, state_indices)`); arbitrary Python callables are not supported.
-    key     : int / (2,) uint32 key -> in-kernel Philox stream (throughput mode); ExplicitNoise -> parity mode.
+    key     : int / host (2,) uint32 key -> in-kernel Philox stream keyed by it (throughput mode); a CUDA (2,) uint32
+              tensor -> the same, with the key read on the device (the traced per-device key of src/VMC.py:20; no host
+              sync; with advance_key=True it is replaced by key + 0x9E3779B97F4A7C15 before use, in place);
+              ExplicitNoise -> parity mode.
     Returns (x, accept_rate) — accept_rate is this process's mean (MCMC.py:38); the cross-device pmean of
-    MCMC.py:39 is done by sample_x.  x is updated IN PLACE when x_init is a CUDA float64 tensor (donated buffer,
-    src/VMC.py:11).  wrap_L applies src/VMC.py:24 inside the kernel.  return_trace adds a dict with per-step
-    accept flags, proposal log p, final log p and per-walker accept counts."""
+    MCMC.py:39 is done by sample_x.  x is updated IN PLACE when x_init is a contiguous CUDA float64 tensor (donated
+    buffer, src/VMC.py:11); any other input is copied and the advanced copy is returned.  wrap_L applies src/VMC.py:24
+    inside the kernel.  return_trace adds a dict with per-step accept flags, proposal log p, final log p and per-walker
+    accept counts.  stats: optional CUDA float64 vector (>= 8) that receives [accepted moves, proposals] (include/cgb200.h)."""
     if not isinstance(logp_fn, BoundLogp):
         raise TypeError("mcmc needs logp.bind(params_flow, state_indices); generic callables have no kernel")
     lg = logp_fn.logp
-    xd, was_np = _to_dev(x_init, torch.float64)
-    B, n = int(xd.shape[0]), int(xd.shape[1])
+    # every argument is validated BEFORE the launch: the kernel advances x in place
+    if wrap_L is not None and abs(float(wrap_L) - lg.L) > 1e-12 * lg.L:
+        raise ValueError("wrap_L must equal the box length the logp was built with")
+    shape = tuple(x_init.shape)
+    if len(shape) != 3 or shape[2] != 2:
+        raise ValueError("x_init must be (batch, n, 2)")
+    B, n = int(shape[0]), int(shape[1])
     S = int(mc_steps)
+    if S < 1:
+        raise ValueError("mc_steps must be >= 1")
     if tuple(logp_fn.state_idx.shape) != (B, n):
         raise ValueError("state_indices bound to logp_fn must be (batch, n)")
-    noise = unif = None
+    xd, was_np = _to_dev(x_init, torch.float64)
+    noise = unif = key_dev = None
     seed = 0
     if isinstance(key, ExplicitNoise):
         noise, _ = _to_dev(key.noise, torch.float64)
         unif, _ = _to_dev(key.uniforms, torch.float64)
         if tuple(noise.shape) != (S, B, n, 2) or tuple(unif.shape) != (S, B):
             raise ValueError("ExplicitNoise shapes must be (mc_steps,batch,n,2) and (mc_steps,batch)")
+    elif _is_device_key(key):
+        key_dev = _device_key(key)
     else:
         seed = _seed_of(key)
+    if advance_key and key_dev is None:
+        raise ValueError("advance_key needs a device key")
+    if stats is not None and (not stats.is_cuda or stats.dtype != torch.float64 or stats.numel() < _lib.STATS_LEN):
+        raise ValueError("stats must be a CUDA float64 tensor with >= %d entries" % _lib.STATS_LEN)
     dev = xd.device
     out_logp = torch.empty(B, dtype=torch.float64, device=dev)
     nacc = torch.empty(B, dtype=torch.int32, device=dev)
     acc_tr = torch.empty((S, B), dtype=torch.uint8, device=dev) if return_trace else None
     lp_tr = torch.empty((S + 1, B), dtype=torch.float64, device=dev) if return_trace else None
     ws = lg.workspace(B, n)
+    flags = _flags() | (_lib.FLAG_ADVANCE_KEY if advance_key else 0)
     check(lib.cgb_mcmc_sweep_f64io(_stream(), _ptr(xd), _ptr(logp_fn.state_idx), _ptr(lg.ktable_dev()), lg.M, lg.twist,
-                                   _ptr(logp_fn.params), _ptr(noise), _ptr(unif), seed, S, float(mc_stddev), lg.L,
-                                   B, n, 0 if wrap_L is None else 1, _ptr(out_logp), _ptr(nacc), _ptr(acc_tr),
-                                   _ptr(lp_tr), _ptr(ws), ws.numel()), "cgb_mcmc_sweep_f64io")
-    if wrap_L is not None and abs(float(wrap_L) - lg.L) > 1e-12 * lg.L:
-        raise ValueError("wrap_L must equal the box length the logp was built with")
+                                   _ptr(logp_fn.params), _ptr(noise), _ptr(unif), seed, _ptr(key_dev), S, float(mc_stddev),
+                                   lg.L, B, n, 0 if wrap_L is None else 1, _ptr(out_logp), _ptr(nacc), _ptr(acc_tr),
+                                   _ptr(lp_tr), _ptr(stats), _ptr(ws), ws.numel(), flags), "cgb_mcmc_sweep_f64io")
+    if not _want_rate:                       # fused sampling step: the rate comes from the statistics vector
+        return xd, None
     accept_rate = nacc.sum(dtype=torch.float64) / (S * B)
     x_out = xd.cpu().numpy() if was_np else xd
     if was_np:
@@ -263,16 +340,32 @@ def sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L):
     jax.pmap): the sweep (VMC.py:23), the wrap into [0,L) (VMC.py:24) and the cross-device mean of the accept
     rate (MCMC.py:39) as one all-reduce over the default process group (NCCL on GPUs).  The VAN draw of
     VMC.py:22 stays with the caller, which passes `state_indices`.  Returns (key', x, accept_rate) where key'
-    is the advanced integer key."""
-    seed = _seed_of(key) if not isinstance(key, ExplicitNoise) else None
-    x, acc = mcmc(logp.bind(params_flow, state_indices), x, key, mc_steps, mc_stddev, wrap_L=L)
+    is the advanced integer key; a device key (CUDA (2,) uint32, one per rank) is advanced in place by the sweep's prologue
+    kernel and returned as is."""
+    dev_key = _is_device_key(key)
+    seed = _seed_of(key) if not (isinstance(key, ExplicitNoise) or dev_key) else None
+    r, w = _world()
+    # the Philox counters are (local walker, step): ranks must not share a key.  The reference carries one key per device
+    # (keys of shape (ndev, 2), main.py:236); an integer key is therefore folded with the rank here, a device key is
+    # per-rank by construction (the caller holds one per GPU).
+    run_key = key if seed is None else _fold_rank(seed, r)
+    x, acc = mcmc(logp.bind(params_flow, state_indices), x, run_key, mc_steps, mc_stddev, wrap_L=L, advance_key=dev_key)
     acc_t = acc if isinstance(acc, torch.Tensor) else torch.tensor(acc, dtype=torch.float64, device=_dev())
-    _, w = _world()
     rate = acc_t                               # equal shards (main.py:231-238): mean of per-device means == global mean
     if w > 1:
         rate = _all_reduce_sum(acc_t.reshape(1).clone())[0] / w
     new_key = key if seed is None else (seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
     return new_key, x, (rate if isinstance(acc, torch.Tensor) else float(rate))
+
+
+def _fold_rank(seed, rank):
+    """jax.random.fold_in analogue for integer keys: rank 0 keeps the key (single-process runs are unchanged)."""
+    if rank == 0:
+        return seed
+    z = (seed + 0x9E3779B97F4A7C15 * (rank + 1)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -337,19 +430,21 @@ class VanSampler:
         Philox; ExplicitGumbel -> parity mode.  Results are CUDA tensors."""
         pd = self._params(params)
         B = int(batch)
-        g, seed = None, 0
+        g, seed, key_dev = None, 0, None
         if isinstance(key, ExplicitGumbel):
             g, _ = _to_dev(key.noise, torch.float64)
             if tuple(g.shape) != (B, self.n, self.M):
                 raise ValueError("ExplicitGumbel noise must be (batch, n, num_states)")
+        elif _is_device_key(key):
+            key_dev = _device_key(key)
         else:
-            seed = _seed_of(key)
+            seed = _fold_rank(_seed_of(key), _world()[0])       # one stream per rank (src/VMC.py:20: per-device keys)
         dev = pd.device
         out = torch.empty((B, self.n), dtype=torch.int32, device=dev)
         lp = torch.empty(B, dtype=torch.float64, device=dev) if return_log_prob else None
         lg = torch.empty((B, self.n, self.M), dtype=torch.float64, device=dev) if return_logits else None
         check(lib.cgb_van_sample_f64io(_stream(), _ptr(pd), self.nparams, _ptr(self._ktable()), self.M, self.n, B, _ptr(g),
-                                       seed, _ptr(out), _ptr(lp), _ptr(lg)), "cgb_van_sample_f64io")
+                                       seed, _ptr(key_dev), _ptr(out), _ptr(lp), _ptr(lg)), "cgb_van_sample_f64io")
         res = [out] + ([lp] if return_log_prob else []) + ([lg] if return_logits else [])
         return res[0] if len(res) == 1 else tuple(res)
 
@@ -382,6 +477,12 @@ def sample_stateindices_and_x(key, sampler, params_van, logp, x, params_flow, mc
     """src/VMC.py:8-25 for THIS process's shard (one process per GPU replaces jax.pmap): key split (VMC.py:20), VAN draw of
     the occupied orbitals (VMC.py:22), Metropolis sweep (VMC.py:23), wrap (VMC.py:24), cross-device mean of the accept rate
     (MCMC.py:39).  `key` is an integer; returns (key', state_indices, x, accept_rate) like the reference."""
+    if _is_device_key(key):
+        # device-resident key: the sampler and the sweep draw from different Philox stream ids of the same key; the sweep's
+        # prologue advances the key in place for the next step (the analogue of VMC.py:20's split)
+        state_indices = sampler(params_van, key, int(x.shape[0]))
+        _, x, rate = sample_x(key, state_indices, logp, x, params_flow, mc_steps, mc_stddev, L)
+        return key, state_indices, x, rate
     seed = _seed_of(key)
     mix = lambda s, c: (s * 6364136223846793005 + c) & 0xFFFFFFFFFFFFFFFF
     key_next, key_state, key_mcmc = mix(seed, 1442695040888963407), mix(seed, 0x9E3779B97F4A7C15), mix(seed, 0xD1B54A32D192ED03)
@@ -421,18 +522,81 @@ def ewald_tables(G, kappa):
     return _EWALD_CACHE[key]
 
 
-def potential_energy(x, kappa, G, L, rs):
+def potential_energy(x, kappa, G, L, rs, stats=None):
     """src/potential.py:69-77 — Ewald energy (coordinate-dependent part) of a batch x (batch, n, 2) -> (batch,).
-    The caller adds Vconst = n*rs/L*Madelung (src/VMC.py:40, main.py:171)."""
+    The caller adds Vconst = n*rs/L*Madelung (src/VMC.py:40, main.py:171).  stats: optional CUDA float64 vector (>= 8)
+    that receives [.., .., sum V, sum V^2, batch] (include/cgb200.h CGB_STATS_*) from the kernel's own epilogue."""
     xd, was_np = _to_dev(x, torch.float64)
     if xd.ndim != 3 or xd.shape[2] != 2:
         raise NotImplementedError("only dim=2 is supported (x must be (batch, n, 2))")
+    if stats is not None and (not stats.is_cuda or stats.dtype != torch.float64 or stats.numel() < _lib.STATS_LEN):
+        raise ValueError("stats must be a CUDA float64 tensor with >= %d entries" % _lib.STATS_LEN)
     items, n_items, gmax = ewald_tables(G, kappa)
     B, n = int(xd.shape[0]), int(xd.shape[1])
     out = torch.empty(B, dtype=torch.float64, device=xd.device)
     check(lib.cgb_ewald_f64io(_stream(), _ptr(xd), B, n, float(L), float(rs), float(kappa), _ptr(items), n_items, gmax,
-                              _ptr(out)), "cgb_ewald_f64io")
+                              _ptr(out), _ptr(stats)), "cgb_ewald_f64io")
     return out.cpu().numpy() if was_np else out
+
+
+class SamplingStep:
+    """One sampling step of the reference's training loop for THIS rank's shard (main.py:334-338 -> src/VMC.py:23-24,40,46-53
+    -> src/MCMC.py): Metropolis sweep + wrap, Ewald energy of the final walkers, and ONE all-reduce of the 5-entry statistics
+    vector [accepted, proposed, sum V, sum V^2, walkers] that the kernels' epilogues fill — 3 kernel launches
+    (prologue, sweep, Ewald) and one collective, all on the current stream, no host synchronisation: the whole step can be
+    captured in a CUDA graph (`capture()`), the per-device PRNG key lives on the device and is advanced by the prologue.
+
+    step() returns the CUDA tensor `stats` (float64, 8 entries; after the all-reduce the sums are over all ranks):
+    accept_rate = stats[0]/stats[1], V_mean = stats[2]/stats[4] + Vconst, ... (see `summary`)."""
+
+    def __init__(self, logp, state_indices, params_flow, x, key, mc_steps, mc_stddev, kappa, G, rs, Vconst=0.0):
+        self.bound = logp.bind(params_flow, state_indices)
+        self.logp, self.x = logp, x
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()):
+            raise ValueError("SamplingStep needs a contiguous CUDA float64 walker tensor (updated in place)")
+        self.key = key if _is_device_key(key) else device_key(_fold_rank(_seed_of(key), _world()[0]), x.device)
+        self.mc_steps, self.mc_stddev = int(mc_steps), float(mc_stddev)
+        self.kappa, self.G, self.rs, self.Vconst = kappa, G, float(rs), float(Vconst)
+        self.stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=x.device)
+        self.V = None
+        self.graph = None
+
+    def _enqueue(self):
+        mcmc(self.bound, self.x, self.key, self.mc_steps, self.mc_stddev, wrap_L=self.logp.L, stats=self.stats,
+             advance_key=True, _want_rate=False)
+        self.V = potential_energy(self.x, self.kappa, self.G, self.logp.L, self.rs, stats=self.stats)
+        _, w = _world()
+        if w > 1:
+            _all_reduce_sum(self.stats[:5])          # the ONE collective of the step (replaces the pmeans of MCMC.py:39, VMC.py:46-53)
+
+    def capture(self, warmup=2):
+        """Capture the step into a CUDA graph (collective included).  Call once; `step()` then replays it."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        return self
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        return self.stats
+
+    def summary(self):
+        """(accept_rate, V_mean, V2_mean) incl. Vconst, as Python floats (synchronises)."""
+        s = self.stats.cpu().numpy()
+        nw = s[4]
+        vm = s[2] / nw + self.Vconst
+        v2 = (s[3] + 2 * self.Vconst * s[2]) / nw + self.Vconst ** 2
+        return float(s[0] / s[1]), float(vm), float(v2)
 
 
 def potential_stats(V):
@@ -469,6 +633,26 @@ class Config:
     @property
     def L(self):
         return float(np.sqrt(np.pi * self.n))      # main.py:67
+
+
+def debug_rng(key, B, S, n, kat=None):
+    """The throughput mode's random streams as the sweep kernels draw them (tests): returns (normal (S,B,n,2) f32,
+    uniform (S,B) f64[, philox blocks (len(kat),4) u32 for kat = (k,6) uint32 rows of counter[4]+key[2]])."""
+    key_dev, seed = (_device_key(key), 0) if _is_device_key(key) else (None, _seed_of(key))
+    nrm = torch.empty((S, B, n, 2), dtype=torch.float32, device=_dev())
+    uni = torch.empty((S, B), dtype=torch.float64, device=_dev())
+    kin = kout = None
+    nk = 0
+    if kat is not None:
+        k = np.ascontiguousarray(np.asarray(kat, dtype=np.uint32).reshape(-1, 6))
+        nk = k.shape[0]
+        kin = torch.as_tensor(k.view(np.int32)).to(_dev())
+        kout = torch.empty((nk, 4), dtype=torch.int32, device=_dev())
+    check(lib.cgb_debug_rng(_stream(), seed, _ptr(key_dev), B, S, n, _ptr(nrm), _ptr(uni), _ptr(kin), _ptr(kout), nk),
+          "cgb_debug_rng")
+    if kat is not None:
+        return nrm, uni, kout.cpu().numpy().view(np.uint32)
+    return nrm, uni
 
 
 def microbench(kind, blocks, iters):

@@ -71,5 +71,39 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ float u32_to_unit_open(uint32_t r) {
     return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
 }
+// the same with a second word behind it: when the top 23 bits are all zero (probability 2^-23) the next 23 bits refine the
+// value, so the lower tail reaches 2^-47 instead of 2^-24 (Box-Muller radius up to 8 sigma instead of 5.8)
+__device__ __forceinline__ float u32x2_to_unit_open(uint32_t hi, uint32_t lo) {
+    const uint32_t k = hi >> 9;
+    return k ? ((float)k + 0.5f) * (1.0f / 8388608.0f) : ((float)(lo >> 9) + 0.5f) * (1.0f / 70368744177664.0f);
+}
+
+// ---- the throughput mode's random streams (shared by every kernel and by the debug export that the statistical tests
+// read): all keyed by (seed; walker, step / draw, particle / orbital, stream id), i.e. independent of the schedule ----------
+// proposal noise of (walker b, step s, particle i): two independent N(0,1) (MCMC.py:26), Box-Muller with accurate logf /
+// sincospif (the approximate __logf has an absolute error that distorts the radius near u = 1)
+__device__ __forceinline__ float2 rng_normal2(uint64_t seed, uint32_t b, uint32_t s, uint32_t i) {
+    const uint4 r = philox4x32_10(make_uint4(b, s, i, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float rad = sqrtf(-2.f * logf(u32x2_to_unit_open(r.x, r.z)));
+    float sn, cs;
+    sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+// Metropolis uniform of (walker b, step s) in [0, 1) with 53 random bits (MCMC.py:29)
+__device__ __forceinline__ double rng_uniform(uint64_t seed, uint32_t b, uint32_t s) {
+    const uint4 r = philox4x32_10(make_uint4(b, s, 0xffffffffu, 1u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return (double)((((unsigned long long)r.x << 32) | (unsigned long long)r.y) >> 11) * (1.0 / 9007199254740992.0);
+}
+// Gumbel noise of (walker b, draw i, orbital j) for the categorical draws of the momentum sampler (sampler.py:36-37)
+__device__ __forceinline__ double rng_gumbel(uint64_t seed, uint32_t b, uint32_t i, uint32_t j) {
+    const uint4 r = philox4x32_10(make_uint4(b, i, j, 2u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return (double)(-logf(-logf(u32x2_to_unit_open(r.x, r.z))));        // u strictly inside (0,1): finite
+}
+// the seed of a call: the host value, or -- when the caller passes a device-resident (2,) uint32 PRNG key, the form a
+// traced jax key has inside pmap (src/VMC.py:20, src/MCMC.py:24) -- key[0] << 32 | key[1] read by the kernel itself
+__device__ __forceinline__ uint64_t rng_seed_of(uint64_t seed_host, const uint32_t* key_dev) {
+    if (key_dev) return ((uint64_t)__ldg(key_dev) << 32) | (uint64_t)__ldg(key_dev + 1);
+    return seed_host;
+}
 
 }  // namespace cgb

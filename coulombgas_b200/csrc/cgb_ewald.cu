@@ -150,6 +150,34 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
             p.out[b] = 2.0 * p.rs * invL * a;                                     // potential.py:77
         }
     }
+    // ---- statistics of the batch (the V_mean / V2_mean entries of the pmean at src/VMC.py:46-53): the LAST CTA to finish
+    // reduces out[0..B) in a fixed order -> deterministic sums, no second kernel, no floating-point atomics
+    if (p.stats) {
+        __shared__ bool s_last;
+        __shared__ double s_red[2][8];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(p.stats + 7), 1ull);
+            s_last = t == (unsigned long long)gridDim.x - 1ull;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double s1 = 0.0, s2 = 0.0;
+            for (int b = threadIdx.x; b < p.B; b += blockDim.x) { const double v = __ldcg(p.out + b); s1 += v; s2 = fma(v, v, s2); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            if (lane == 0) { s_red[0][warp] = s1; s_red[1][warp] = s2; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t1 = 0.0, t2 = 0.0;
+                for (int w = 0; w < nwarps; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+                p.stats[CGB_STATS_SUM_V] = t1; p.stats[CGB_STATS_SUM_V2] = t2; p.stats[CGB_STATS_NWALKERS] = (double)p.B;
+                *reinterpret_cast<unsigned long long*>(p.stats + 7) = 0ull;
+            }
+        }
+    }
 }
 
 int launch_ewald(const EwaldParams& p, cudaStream_t st) {
@@ -218,6 +246,36 @@ __global__ void __launch_bounds__(256) microbench_kernel(int kind, int iters, fl
 
 int launch_microbench(int kind, int blocks, int iters, float* out, cudaStream_t st) {
     microbench_kernel<<<blocks, 256, 0, st>>>(kind, iters, out);
+    return (int)cudaGetLastError();
+}
+
+// ---- debug export of the throughput mode's random streams (tests: Philox known answers, moments / KS of the draws) -------
+// out_normal (S,B,n,2) f32 and out_uniform (S,B) f64: exactly what the sweep kernels draw for (walker b, step s + 1, particle i);
+// kat_in / kat_out (n_kat x 6 / x 4 words): raw Philox4x32-10 blocks for given (counter[4], key[2]).
+__global__ void rng_dump_kernel(uint64_t seed_host, const uint32_t* key_dev, int B, int S, int n, float* out_normal,
+                                double* out_uniform, const uint32_t* kat_in, uint32_t* kat_out, int n_kat) {
+    const uint64_t seed = rng_seed_of(seed_host, key_dev);
+    const size_t total = (size_t)S * B * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t % n);
+        const size_t sb = t / n;
+        const int b = (int)(sb % B), s = (int)(sb / B);
+        if (out_normal) {
+            const float2 g = rng_normal2(seed, (uint32_t)b, (uint32_t)(s + 1), (uint32_t)i);
+            out_normal[2 * t] = g.x; out_normal[2 * t + 1] = g.y;
+        }
+        if (out_uniform && i == 0) out_uniform[sb] = rng_uniform(seed, (uint32_t)b, (uint32_t)(s + 1));
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_kat; t += gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4(kat_in[6 * t], kat_in[6 * t + 1], kat_in[6 * t + 2], kat_in[6 * t + 3]),
+                                      make_uint2(kat_in[6 * t + 4], kat_in[6 * t + 5]));
+        kat_out[4 * t] = r.x; kat_out[4 * t + 1] = r.y; kat_out[4 * t + 2] = r.z; kat_out[4 * t + 3] = r.w;
+    }
+}
+
+int launch_rng_dump(uint64_t seed, const uint32_t* key_dev, int B, int S, int n, float* out_normal, double* out_uniform,
+                    const uint32_t* kat_in, uint32_t* kat_out, int n_kat, cudaStream_t st) {
+    rng_dump_kernel<<<592, 256, 0, st>>>(seed, key_dev, B, S, n, out_normal, out_uniform, kat_in, kat_out, n_kat);
     return (int)cudaGetLastError();
 }
 

@@ -32,7 +32,8 @@ struct SweepParams {
     const double* params;     // the caller's flat float64 parameters (forward pass of the single-particle stream)
     const double* noise;      // (S,B,n,2) or null
     const double* uniforms;   // (S,B) or null
-    uint64_t seed;
+    uint64_t seed;            // throughput mode: Philox key (host value) ...
+    const uint32_t* key_dev;  // ... or, when non-null, a device-resident (2,) uint32 PRNG key read by the kernel (key[0] << 32 | key[1])
     int mc_steps;
     double sigma;
     double L;
@@ -44,6 +45,10 @@ struct SweepParams {
     double* out_parts;        // (B,2) or null
     float* out_jac;           // (B,2n,2n) or null
     int force_pivot;          // debug: always use the pivoted scalar LU for the Jacobian
+    int force_f64_slater;     // debug: always use the float64 Slater LU (warp kernel)
+    float slater32_errsum_max;    // FP32 Slater LU is kept while sum_k k / |u_kk|^2 stays below this (else redone in float64)
+    double* out_stats;        // CGB_STATS_LEN doubles or null: [0] += accepted moves per walker (zeroed by the prologue)
+    int advance_key;          // prologue: key_dev += golden-ratio increment before the sweep reads it
     unsigned long long* fallback_counter;   // evaluations redone with the pivoted LU (in the workspace)
     // ---- warp-per-walker kernel only (cgb_wsweep.cu): per-call scheduler state in the caller's workspace
     const void* wconst;           // staging copy of the constant-bank weight block (device)
@@ -54,13 +59,15 @@ struct SweepParams {
     double* ws_logp;              // (B) current log p per walker
     int* ws_nacc;                 // (B) accepted moves so far
     int cspec;                    // CTA kernel's speculative mode: -1 = auto (widest tree that fits), 0 = off, 4/8 = CTAs per walker
+    unsigned long long* prof;     // developer builds (CGBW_PROF): 12 per-phase cycle sums in the workspace, else unused
     int spec;                     // 4 / 8: speculative mode, warps per walker (one CTA evaluates the next 2-3 / 3-4 steps' proposals at once)
 };
 
 // workspace layout (bytes); the B-dependent arrays start at WS_DYN
 enum : size_t {
     WS_WPACK = 0,           // W_TOTAL floats (CTA-per-walker kernel)
-    WS_CTR = 4096,          // +0: pivot-fallback counter (u64, cumulative); +64: queue head, tail, spin diagnostics (3 x u64)
+    WS_CTR = 4096,          // +0: pivot-fallback counter (u64, cumulative); +8: float64-Slater-fallback counter; +64: queue head, tail, spin diagnostics (3 x u64);
+                            // +128: 12 x u64 per-phase cycle sums (developer builds with CGBW_PROF only)
     WS_WCONST = 4352,       // staging copy of the constant-bank weight block (warp-per-walker kernel)
     WS_DYN = 4352 + 11264
 };
@@ -74,7 +81,7 @@ inline size_t ws_total_bytes(int B) {
 inline int sweep_num_warps(int n) { int w = (n + 7) / 8; return w < 2 ? 2 : w; }
 size_t sweep_smem_bytes(int n);
 int launch_sweep(const SweepParams& p, cudaStream_t st);
-int launch_prep_params(const double* params, float* wpack, cudaStream_t st);
+int launch_prep_params(const SweepParams& p, float* wpack, cudaStream_t st);      // + stats zero, key advance
 // warp-per-walker sweep (n <= 32, instantiated shapes only): returns CGB_E_UNSUPPORTED when n has no instance
 bool wsweep_supported(int n);
 int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st);
@@ -84,9 +91,12 @@ struct EwaldParams {
     const double* x; int B, n; double L, rs, kappa;
     const float4* items; int n_items, gmax;
     double* out;
+    double* stats;                // CGB_STATS_LEN doubles or null: [2] sum V, [3] sum V^2, [4] B; [7] scratch counter
 };
 int launch_ewald(const EwaldParams& p, cudaStream_t st);
 int launch_microbench(int kind, int blocks, int iters, float* out, cudaStream_t st);
+int launch_rng_dump(uint64_t seed, const uint32_t* key_dev, int B, int S, int n, float* out_normal, double* out_uniform,
+                    const uint32_t* kat_in, uint32_t* kat_out, int n_kat, cudaStream_t st);
 
 // autoregressive momentum sampler (cgb_van.cu)
 struct VanParams {
@@ -94,6 +104,7 @@ struct VanParams {
     const int32_t* state_in;      // (B,n) or null: given choices (log_prob mode)
     const double* gumbel;         // (B,n,M) or null
     uint64_t seed;
+    const uint32_t* key_dev;      // device-resident (2,) uint32 key (overrides seed), or null
     int32_t* out_state;           // (B,n) or null
     double* out_logprob;          // (B) or null
     double* out_logits;           // (B,n,M) masked logits, or null

@@ -23,7 +23,15 @@ namespace cgb {
 // ---------------------------------------------------------------------------------------------------
 // parameter packing: float64 haiku-order vector -> FP32 kernel layout (Wt, bt pre-scaled by log2 e)
 // ---------------------------------------------------------------------------------------------------
-__global__ void prep_params_kernel(const double* __restrict__ p, float* __restrict__ w) {
+__global__ void prep_params_kernel(const double* __restrict__ p, float* __restrict__ w, double* stats, double nprop,
+                                   uint32_t* key_dev, int advance_key) {
+    if (threadIdx.x == 0) {       // prologue duties of the sampling step (include/cgb200.h: CGB_STATS_*, CGB_FLAG_ADVANCE_KEY)
+        if (stats) { for (int t = 0; t < CGB_STATS_LEN; ++t) stats[t] = 0.0; stats[CGB_STATS_NPROPOSED] = nprop; }
+        if (key_dev && advance_key) {
+            const uint64_t k = (((uint64_t)key_dev[0] << 32) | (uint64_t)key_dev[1]) + 0x9E3779B97F4A7C15ull;
+            key_dev[0] = (uint32_t)(k >> 32); key_dev[1] = (uint32_t)k;
+        }
+    }
     // source offsets in the flat 1074 vector (include/cgb200.h)
     const int S_WT = 0, S_BT = 80, S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
     for (int t = threadIdx.x; t < W_TOTAL; t += blockDim.x) {
@@ -226,18 +234,12 @@ sweep_kernel(const SweepParams p) {
     // (walker, step, particle) -- independent of who asks and when
     auto noise_of = [&](const int b, const int st) -> double {
         if (p.noise) return p.noise[((size_t)(st - 1) * p.B + b) * N2 + tid];
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)st, (uint32_t)(tid >> 1), 0u),
-                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-        const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
-        float sn, cs;
-        sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
-        return (double)(rad * ((tid & 1) ? sn : cs));
+        const float2 g = rng_normal2(rng_seed_of(p.seed, p.key_dev), (uint32_t)b, (uint32_t)st, (uint32_t)(tid >> 1));
+        return (double)((tid & 1) ? g.y : g.x);
     };
     auto uniform_of = [&](const int b, const int st) -> double {                 // MCMC.py:29
         if (p.uniforms) return p.uniforms[(size_t)(st - 1) * p.B + b];
-        const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)st, 0xffffffffu, 1u),
-                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-        return ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
+        return rng_uniform(rng_seed_of(p.seed, p.key_dev), (uint32_t)b, (uint32_t)st);
     };
     constexpr int CW = SPECC ? SPECC : 1;                    // CTAs per walker
     const int crank = SPECC ? (int)cluster_ctarank() : 0;
@@ -987,6 +989,7 @@ sweep_kernel(const SweepParams p) {
         if (tid == 0 && crank == 0) {
             if (p.out_logp) p.out_logp[b] = logp_cur;
             if (p.out_naccept) p.out_naccept[b] = nacc;
+            if (p.out_stats && p.mc_steps > 0) atomicAdd(p.out_stats + CGB_STATS_NACCEPT, (double)nacc);   // integers: exact, order-free
         }
     }
     if constexpr (SPECC != 0) cluster_sync_all();     // no CTA leaves while a neighbour may still read its log p slots
@@ -1052,8 +1055,9 @@ int launch_sweep(const SweepParams& p, cudaStream_t st) {
     }
 }
 
-int launch_prep_params(const double* params, float* wpack, cudaStream_t st) {
-    prep_params_kernel<<<1, 256, 0, st>>>(params, wpack);
+int launch_prep_params(const SweepParams& p, float* wpack, cudaStream_t st) {
+    prep_params_kernel<<<1, 256, 0, st>>>(p.params, wpack, p.out_stats, (double)p.B * (double)p.mc_steps,
+                                          const_cast<uint32_t*>(p.key_dev), p.advance_key);
     return (int)cudaGetLastError();
 }
 

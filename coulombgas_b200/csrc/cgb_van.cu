@@ -212,9 +212,7 @@ __global__ void __launch_bounds__(256) van_kernel(const VanParams p) {
                         double g;
                         if (p.gumbel) g = __ldg(p.gumbel + ((size_t)b * n + i) * M + j);
                         else {
-                            const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)i, (uint32_t)j, 2u),
-                                                           make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                            g = (double)(-__logf(-__logf(u32_to_unit_open(rr.x))));   // u strictly inside (0,1): g finite
+                            g = rng_gumbel(rng_seed_of(p.seed, p.key_dev), (uint32_t)b, (uint32_t)i, (uint32_t)j);
                         }
                         const double v = a + g;
                         if (ok && v > best) { best = v; bestj = j; } // first maximum inside the lane (j ascending); masked

@@ -28,6 +28,7 @@
 // Slater matrix and LU, float64 log-det sums and Metropolis test.
 #include "cgb_common.cuh"
 #include <stdlib.h>
+#include <mutex>
 #include "cgb_internal.h"
 
 namespace cgb {
@@ -43,6 +44,8 @@ struct WConst {
     float w1b[16][16];    // W1[16:32]         acts on mean_k h_k
     float w1c[16][16];    // W1[32:48]         acts on mean_j t_ij
     float wf[16][2];      // Wf
+    float sabM[16];       // pass 1: magic constant 2^e >= max |a_c| of channel c (fixed-point accumulation of sum_k |a_k|)
+    double sabS[16];      // ... and the weight 2^(e-23) of one unit of that fixed-point sum
     double dw0c[5][16];
     double db0[16];
     double dw1a[16][16];
@@ -53,7 +56,26 @@ struct WConst {
 static_assert(sizeof(WConst) <= 11264, "WS_WCONST staging area too small");
 __constant__ WConst cW;
 
-__global__ void prep_wconst_kernel(const double* __restrict__ p, WConst* __restrict__ w) {
+// Prologue of a sweep, ONE launch: weight block, ready queue (all walkers ready for step 0), per-walker step counters,
+// statistics vector, device key advance.
+__global__ void wsweep_prologue_kernel(const double* __restrict__ p, WConst* __restrict__ w, unsigned long long* slots,
+                                       unsigned cap, unsigned B, unsigned long long* ctr, int* done, double* stats, double nprop,
+                                       uint32_t* key_dev, int advance_key) {
+    {   // ready queue (bounded MPMC, Vyukov style): slot = (sequence << 32) | walker.  Slot i starts "filled" with walker i
+        // for i < B and "free for push i" otherwise; head = 0, tail = B.  cap == 0: speculative mode, no queue.
+        const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < cap) slots[i] = i < B ? (((unsigned long long)(i + 1) << 32) | i) : ((unsigned long long)i << 32);
+        if (cap && i < B) done[i] = 0;
+        if (i == 0) {
+            if (cap) { ctr[0] = 0ull; ctr[1] = (unsigned long long)B; ctr[2] = 0ull; }    // head, tail, spin diagnostics
+            if (stats) { for (int t = 0; t < CGB_STATS_LEN; ++t) stats[t] = 0.0; stats[CGB_STATS_NPROPOSED] = nprop; }
+            if (key_dev && advance_key) {
+                const uint64_t k = (((uint64_t)key_dev[0] << 32) | (uint64_t)key_dev[1]) + 0x9E3779B97F4A7C15ull;
+                key_dev[0] = (uint32_t)(k >> 32); key_dev[1] = (uint32_t)k;
+            }
+        }
+    }
+    if (blockIdx.x != 0) return;
     // source offsets in the flat 1074 vector (include/cgb200.h)
     constexpr int S_WT = 0, S_BT = 80, S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
     constexpr double LOG2E = 1.4426950408889634;
@@ -63,6 +85,16 @@ __global__ void prep_wconst_kernel(const double* __restrict__ p, WConst* __restr
         (&w->dw0c[0][0])[t] = p[S_W0 + 64 + t];
     }
     for (int t = threadIdx.x; t < 16; t += blockDim.x) {
+        {   // |a_c| <= |bt| + |Wt0| + |Wt1| + |Wt2| + |Wt3| + sqrt(2) |Wt4|  (features: cos, cos, sin, sin, d <= sqrt 2; log2 units)
+            double A = fabs(p[S_BT + t]);
+            for (int f = 0; f < 5; ++f) A += fabs(p[S_WT + 16 * f + t]) * (f == 4 ? 1.4142135623730951 : 1.0);
+            A = fmax(A * LOG2E * 1.0001, 1e-30);
+            int e = 0;
+            frexp(A, &e);                        // A = m 2^e, m in [0.5, 1)  ->  2^e > A
+            e = e < -100 ? -100 : (e > 100 ? 100 : e);
+            w->sabM[t] = (float)ldexp(1.0, e);
+            w->sabS[t] = ldexp(1.0, e - 23);
+        }
         w->bt[t] = (float)(p[S_BT + t] * LOG2E);
         w->db0[t] = p[S_B0 + t];
         w->db1[t] = p[S_B1 + t];
@@ -105,6 +137,7 @@ struct WLay {
     // staged Slater rows double2[N][PB]
     static constexpr int MMAX_TAB = (RJ / (16 * N) - 1) / 2 - 1;
     static_assert(16 * N * PB <= RJ, "Slater staging must fit the J region");
+    static_assert(16 * ((N + 18) & ~1) <= H_bytes, "FP32 Slater pivot lines must fit the H region");
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -155,6 +188,20 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 #ifndef CGBW_PACK_PRE23
 #define CGBW_PACK_PRE23 1   // the same for the pre-activations of pass 2+3: +0.9 %
 #endif
+#ifndef CGBW_UFORM
+#define CGBW_UFORM 1        // pass 2+3: accumulate U = Q + sum_c (sigma'_c R_c) Wt_c^T (2x5) and contract with E once per pair
+#endif
+#ifndef CGBW_PROF
+#define CGBW_PROF 0         // 1: developer build that accumulates per-phase cycle counts of every warp (tools/phase_clocks.py)
+#endif
+#if CGBW_PROF
+#define PROF_MARK(i) do { if (lane == 0) { const long long t_ = clock64(); s_prof[threadIdx.x >> 5][i] += (unsigned long long)(t_ - s_prof_t0[threadIdx.x >> 5]); s_prof_t0[threadIdx.x >> 5] = t_; } } while (0)
+#else
+#define PROF_MARK(i) do { } while (0)
+#endif
+#ifndef CGBW_FIXSUM
+#define CGBW_FIXSUM 1       // pass 1: sum_k |a_k| and sum_k d_k in 32-bit fixed point (FADD with a magic constant + IADD) instead of
+#endif                      // F2F + DADD per term (the conversions run on the quarter-rate XU pipe); trig feature sums separable
 #ifndef CGBW_WPC
 #define CGBW_WPC 4          // warps per CTA of the ready-queue kernel (12 / CGBW_WPC CTAs per SM)
 #endif
@@ -262,15 +309,6 @@ __device__ __noinline__ float pivoted_lu_smem(float* Jf, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// ready queue (bounded MPMC, Vyukov style): slot = (sequence << 32) | walker.  Slot i starts "filled" with walker i
-// for i < B (every walker is ready for step 0) and "free for push i" otherwise; head = 0, tail = B.
-__global__ void wqueue_init_kernel(unsigned long long* slots, unsigned cap, unsigned B, unsigned long long* ctr) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap) slots[i] = i < B ? (((unsigned long long)(i + 1) << 32) | i) : ((unsigned long long)i << 32);
-    if (i == 0) { ctr[0] = 0ull; ctr[1] = (unsigned long long)B; ctr[2] = 0ull; }    // head, tail, spin diagnostics
-}
-
-// ---------------------------------------------------------------------------------------------------
 // CTA-shared float64 weights of the forward single-particle stream, regrouped [c4][e][kk] (output channel c = 4 c4 + kk)
 // so that one group of 4 output channels reads contiguous 32-byte rows by broadcast LDS.128.  (As runtime-indexed
 // constant-bank loads these 8 kB thrashed the constant cache: 16 % of all stall samples on 2 % of the instructions.)
@@ -280,6 +318,165 @@ struct WShared {
     double w0c[4][5][4];
 };
 constexpr int W_SHARED_BYTES = ((sizeof(WShared) + 15) & ~15) + 128;      // + the speculative mode's log p exchange slots
+
+// Float64 Slater log-determinant (fallback of the FP32 factorisation of the main kernel, and the path for wave vectors
+// beyond the power tables): row r = lane r, partially pivoted complex LU with implicit row exchange, register-resident,
+// shift-left (the active column is always register 0).  After its first update every unfinished row offers its new
+// register 0; one REDUX picks the next pivot row, whose pivot is shuffled to all lanes (FP32-seeded reciprocal + one float64
+// Newton step) and whose row is published through the shared-memory line.  Returns log|det| (without the L^-n factor), -inf for
+// a singular matrix (slater.py:18).
+template <int N>
+__device__ __noinline__ double slater_logdet_f64(unsigned char* sm, const int2* sK, const int lane, const int kself, const bool rv,
+                                                 const int mmax, const double wx, const double wy) {
+    using L_ = WLay<N>;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int PB = L_::PB;
+    double2* const sPt = reinterpret_cast<double2*>(sm + L_::o_J);
+    __syncwarp();
+    double aD;
+    {
+    double2 Dr[N];
+        if (mmax <= L_::MMAX_TAB) {
+            const int PT = (2 * (mmax + 1)) | 1;
+            double2* tb = sPt + kself * PT;
+            if (rv) {
+#pragma unroll 1
+                for (int comp = 0; comp < 2; ++comp) {
+                    const double wv = comp ? wy : wx;
+                    double sn, cs;
+                    sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
+                    double2* t = tb + comp * (mmax + 1);
+                    double2 pw = make_double2(1.0, 0.0);
+                    t[0] = pw;
+                    for (int m = 1; m <= mmax; ++m) {
+                        pw = make_double2(pw.x * cs - pw.y * sn, pw.x * sn + pw.y * cs);
+                        t[m] = pw;
+                    }
+                }
+            }
+            __syncwarp();
+            const double2* ty = tb + (mmax + 1);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const int2 mk = sK[j];
+                double2 X = tb[abs(mk.x)], Y = ty[abs(mk.y)];
+                X.y = mk.x < 0 ? -X.y : X.y;
+                Y.y = mk.y < 0 ? -Y.y : Y.y;
+                Dr[j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+            }
+        } else {
+            double2* row = sPt + kself * PB;
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) {
+                const int2 mk = sK[j];
+                double ph = fma((double)mk.x, wx, (double)mk.y * wy);
+                ph -= rint(ph);
+                double sn, cs;
+                sincospi(2.0 * ph, &sn, &cs);
+                if (rv) row[j] = make_double2(cs, sn);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < N; ++j) Dr[j] = row[j];
+        }
+        __syncwarp();     // H region (lines) free, tables read
+
+        // ---------------- Slater LU: partially pivoted, implicit row exchange, register-resident, rolled ---------
+        // Same shift-left scheme: the active column is register 0.  After its first update every unfinished
+        // row offers its new register 0; one REDUX picks the next pivot row, which publishes 1/pivot (the
+        // reciprocal chain overlaps the remaining updates) and then its row.  Finished rows compute garbage.
+        bool done = !rv, singular = false;
+        double mypn = 1.0;
+        constexpr int LP = N + 8;
+        double2* const dline0 = reinterpret_cast<double2*>(sm + L_::o_H);    // [2][LP]
+        auto offer = [&](const double2 e) -> unsigned {
+            const float mag = (float)(fabs(e.x) + fabs(e.y));
+            const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x1Fu) | (unsigned)lane);
+            return __reduce_max_sync(FULL, key);
+        };
+        // 1/pivot, computed by EVERY lane from the shuffled pivot (no divergent branch, no shared-memory round trip):
+        // FP32 seed of 1/|e|^2 from the FP32-rounded entry + one float64 Newton step (2^-23 squared)
+        double pn = 1.0;
+        auto pivot_inv = [&](const double2 e) -> double2 {
+            pn = fma(e.x, e.x, e.y * e.y);
+            const float ex = (float)e.x, ey = (float)e.y;
+            const double r0 = (double)rcp_approx(fmaf(ex, ex, ey * ey));
+            const double ip = r0 * (2.0 - pn * r0);
+            return make_double2(e.x * ip, -e.y * ip);
+        };
+        unsigned wk = offer(Dr[0]);
+        double2 iv = pivot_inv(shfl2dw(Dr[0], (int)(wk & 31u)));
+        bool win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
+        if (win) {
+            mypn = pn;
+#pragma unroll
+            for (int j = 1; j < N; ++j) dline0[j] = Dr[j];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            const double2* cur = dline0 + (k & 1) * LP;
+            double2* nxt = dline0 + ((k + 1) & 1) * LP;
+            const unsigned dcur32 = (unsigned)__cvta_generic_to_shared(cur);
+            const int lim = N - 1 - k;
+            singular |= (wk >> 5) == 0u;
+            done |= win;
+            if (lim == 0) break;
+            const double2 c = Dr[0];
+            const double lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
+            const double ly = -(c.x * iv.y + c.y * iv.x);
+            double2 pq[4] = {cur[1], cur[2], cur[3], cur[4]};
+#pragma unroll
+            for (int j0 = 1; j0 < N; j0 += 4) {
+                if (j0 > lim) break;
+                double2 nq[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#if CGBW_PIN_LDS
+                    nq[t] = lds_pinned_d2(dcur32 + 16u * (unsigned)(j0 + 4 + t));
+#else
+                    nq[t] = cur[j0 + 4 + t];
+#endif
+#pragma unroll
+                for (int t = 0; t < 4; ++t)                               // independent first halves (written straight to the
+                    if (j0 + t < N) {                                     // shifted slot): covers the DFMA latency
+                        const double2 o = Dr[j0 + t];
+                        Dr[j0 + t - 1] = make_double2(fma(-ly, pq[t].y, o.x), fma(ly, pq[t].x, o.y));
+                    }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int j = j0 + t;
+                    if (j < N) {
+                        double2 v = Dr[j - 1];
+                        v.x = fma(lx, pq[t].x, v.x);
+                        v.y = fma(lx, pq[t].y, v.y);
+                        Dr[j - 1] = v;
+                        if (j == 1) {
+                            wk = offer(v);
+                            iv = pivot_inv(shfl2dw(v, (int)(wk & 31u)));
+                            win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
+                            if (win) mypn = pn;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) pq[t] = nq[t];
+            }
+            if (win) {
+#pragma unroll
+                for (int j = 1; j < N - 1; ++j) {
+                    if ((j & 3) == 1 && j >= lim) break;
+                    nxt[j] = Dr[j];
+                }
+            }
+            __syncwarp();
+        }
+        aD = (rv && mypn != 1.0) ? 0.5 * log(mypn) : 0.0;
+        aD = warp_sum_f64(aD);
+        if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
+    }
+    return aD;
+}
 
 // SPECW = 4 or 8: speculative ("prefetching") Metropolis for batches that leave most warp slots empty (SPECW = 0: the
 // ready-queue kernel).  One CTA of SPECW warps owns one walker for the whole sweep; per round the warps evaluate,
@@ -296,6 +493,11 @@ wsweep_kernel(const SweepParams p) {
     constexpr bool SPEC = SPECW != 0;
     static_assert(SPECW == 0 || SPECW == 4 || SPECW == 8, "speculation tree: 4 or 8 warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#if CGBW_PROF
+    __shared__ unsigned long long s_prof[8][12];
+    __shared__ long long s_prof_t0[8];
+    if (threadIdx.x < 96) (&s_prof[0][0])[threadIdx.x] = 0ull;
+#endif
     using L_ = WLay<N>;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int PB = L_::PB;
@@ -340,7 +542,9 @@ wsweep_kernel(const SweepParams p) {
     const float invn = 1.f / (float)N;
     const double invL = 1.0 / p.L;
     const double nlogL = (double)N * log(p.L);               // D carries L^{-dim/2} per entry (slater.py:17)
-    const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
+    // (2 pi / L) / n, pinned in a register (result of a shuffle): at the register cap ptxas otherwise rematerialises the
+    // float64 product + conversion inside the pair loops
+    const float alpha = __shfl_sync(0xffffffffu, (float)(2.0 * 3.14159265358979323846 * invL) * invn, 0);
     const unsigned long long total = (unsigned long long)p.B * (unsigned long long)(p.mc_steps + 1);
     const unsigned long long qmask = (unsigned long long)p.qcap - 1ull;
 
@@ -353,21 +557,15 @@ wsweep_kernel(const SweepParams p) {
             if (rv) nz = __ldg(reinterpret_cast<const double2*>(p.noise + (((size_t)(s - 1) * p.B + b) * N + lane) * 2));
             nzx = nz.x; nzy = nz.y;
         } else {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)s, (uint32_t)lane, 0u),
-                                          make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-            const float rad = sqrtf(-2.f * __logf(u32_to_unit_open(r.x)));
-            float sn, cs;
-            sincospif(2.f * u32_to_unit_open(r.y), &sn, &cs);
-            nzx = (double)(rad * cs); nzy = (double)(rad * sn);
+            const float2 g = rng_normal2(rng_seed_of(p.seed, p.key_dev), (uint32_t)b, (uint32_t)s, (uint32_t)lane);
+            nzx = (double)g.x; nzy = (double)g.y;
         }
         xq.x += p.sigma * nzx;
         xq.y += p.sigma * nzy;
     };
     auto uniform_of = [&](const int b, const int s) -> double {                    // MCMC.py:29
         if (p.uniforms) return __ldg(p.uniforms + (size_t)(s - 1) * p.B + b);
-        const uint4 rr = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)s, 0xffffffffu, 1u),
-                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-        return ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);
+        return rng_uniform(rng_seed_of(p.seed, p.key_dev), (uint32_t)b, (uint32_t)s);
     };
 
     // speculative mode: the walker's chain state, replicated identically in the four warps of the CTA
@@ -377,6 +575,9 @@ wsweep_kernel(const SweepParams p) {
     double sp_logp = 0.0;
     double* const sLp = reinterpret_cast<double*>(smem_raw + W_SHARED_BYTES - 128);    // [2][8] log p of the round's nodes
 
+#if CGBW_PROF
+    if (lane == 0) s_prof_t0[threadIdx.x >> 5] = clock64();
+#endif
     for (;;) {
         int b = 0, step = 0;
         bool active = true;
@@ -444,6 +645,9 @@ wsweep_kernel(const SweepParams p) {
         if (step > 0) add_noise(xv, b, step);
         }
         double lp = 0.0, ldD = 0.0, aJ = 0.0;
+#ifdef CGBW_DIAG_ERRSUM
+        double aJ_diag = 0.0;
+#endif
         if (!SPEC || active) {
         // ---------------- reduced coordinates, occupied k rows ------------------------------------------------
         int mmax;
@@ -479,6 +683,7 @@ wsweep_kernel(const SweepParams p) {
         const float2 npc = make_float2(-pos.x, -pos.y);
         __syncwarp();
 
+        PROF_MARK(0);
         // ---------------- pass 1: two-particle stream, means over partners (flow.py:34-36,46) ----------------
         double dzx = 0.0, dzy = 0.0;
         {
@@ -487,6 +692,57 @@ wsweep_kernel(const SweepParams p) {
                 // sum_k softplus2(a_k) = 1/2 (sum_k a_k + sum_k |a_k|) + log2 prod_k (1 + 2^-|a_k|):
                 //   sum_k a_k follows from the feature sums (linear), sum_k |a_k| is accumulated in float64, and the product
                 //   (29 factors in (1,2]) is one FFMA per term -- ONE logarithm per channel and evaluation instead of 29.
+#if CGBW_FIXSUM
+                // Fixed-point partner sums: t = |a| + M with M = 2^e > max |a| (bound from the weights, prologue kernel) has the
+                // value |a| / 2^(e-23) in its mantissa field, and float bit patterns are linear in [M, 2M]: the INTEGER sum of the
+                // bit patterns minus N bits(M) is sum_k |a_k| in units of 2^(e-23), exactly (mod 2^32 arithmetic).  One FADD + one
+                // IADD per term instead of F2F + DADD; the rounding of |a| to the 2^(e-23) grid (e = 4: 2e-6) is below the FP32
+                // error a_k carries already.  The four trigonometric feature sums are separable,
+                //   sum_k cos(th_i - th_k) = cos th_i C + sin th_i S,   C = sum_k cos th_k, S = sum_k sin th_k  (float64 warp sums),
+                // and need no pair loop at all; sum_k d_ik uses the same fixed-point scheme with M = 2 (d <= sqrt 2).
+                double m0s[5];
+                unsigned sabi[16], sdi = 0u;
+                float P[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { sabi[c] = 0u; P[c] = 1.f; }
+                {
+                    const float cthx = fmaf(-2.f * pos.z, pos.z, 1.f), sthx = 2.f * pos.z * pos.x;     // full angles 2 pi u
+                    const float cthy = fmaf(-2.f * pos.w, pos.w, 1.f), sthy = 2.f * pos.w * pos.y;
+                    const double Cx = warp_sum_f64(rv ? (double)cthx : 0.0), Sx = warp_sum_f64(rv ? (double)sthx : 0.0);
+                    const double Cy = warp_sum_f64(rv ? (double)cthy : 0.0), Sy = warp_sum_f64(rv ? (double)sthy : 0.0);
+                    m0s[0] = fma((double)cthx, Cx, (double)sthx * Sx); m0s[1] = fma((double)cthy, Cy, (double)sthy * Sy);
+                    m0s[2] = fma((double)sthx, Cx, -(double)cthx * Sx); m0s[3] = fma((double)sthy, Cy, -(double)cthy * Sy);
+                }
+                float btr[16];                                    // biases in registers (an FFMA takes one constant operand)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) btr[c] = cW.bt[c];
+                float4 pn = sPos[0];
+#pragma unroll 2
+                for (int k = 0; k < N; ++k) {
+                    const WPairFeat f = wpair_features(pos, npc, pn);
+                    pn = sPos[k + 1 < N ? k + 1 : k];             // next partner's table entry ahead of its use
+                    const float d = sqrt_approx(f.d2);            // 0 on the diagonal (flow.py:25)
+                    sdi += __float_as_uint(d + 2.0f);
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) {              // pre-activations of a channel pair through packed FMAs
+                        const int c = 2 * c2;
+                        const float2 a2 = ffma2s(d, make_float2(cW.wt[4][c], cW.wt[4][c + 1]),
+                                          ffma2s(f.s.y, make_float2(cW.wt[3][c], cW.wt[3][c + 1]),
+                                          ffma2s(f.s.x, make_float2(cW.wt[2][c], cW.wt[2][c + 1]),
+                                          ffma2s(f.c.y, make_float2(cW.wt[1][c], cW.wt[1][c + 1]),
+                                          ffma2s(f.c.x, make_float2(cW.wt[0][c], cW.wt[0][c + 1]), make_float2(btr[c], btr[c + 1]))))));
+                        sabi[c] += __float_as_uint(fabsf(a2.x) + cW.sabM[c]);
+                        P[c] = fmaf(P[c], ex2_approx(-fabsf(a2.x)), P[c]);
+                        sabi[c + 1] += __float_as_uint(fabsf(a2.y) + cW.sabM[c + 1]);
+                        P[c + 1] = fmaf(P[c + 1], ex2_approx(-fabsf(a2.y)), P[c + 1]);
+                    }
+                }
+                m0s[4] = (double)(int)(sdi - (unsigned)N * 0x40000000u) * (1.0 / 4194304.0);      // units of 2^-22
+                double sab[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    sab[c] = (double)(int)(sabi[c] - (unsigned)N * __float_as_uint(cW.sabM[c])) * cW.sabS[c];
+#else
                 double sab[16], m0s[5];
                 float P[16];
 #pragma unroll
@@ -528,6 +784,7 @@ wsweep_kernel(const SweepParams p) {
                     }
 #endif
                 }
+#endif
                 const double invnd = 1.0 / (double)N;
 #pragma unroll
                 for (int f = 0; f < 5; ++f) m0d[f] = m0s[f] * invnd;
@@ -542,6 +799,7 @@ wsweep_kernel(const SweepParams p) {
                     md[c] = (0.5 * (sa + sab[c]) + lg) * (0.693147180559945309417 * invnd);
                 }
             }
+            PROF_MARK(1);
             // ---------------- single-particle stream (flow.py:45,51-55): forward values in float64 -----------
             // rolled over groups of 4 output channels (uniform constant-bank indices)
 #pragma unroll 1
@@ -617,6 +875,7 @@ wsweep_kernel(const SweepParams p) {
         }
         __syncwarp();
 
+        PROF_MARK(2);
         // ---------------- pass 2b: H_i = d hbar / d x_i = (1/n) [ sum_k P_k E_ki - P_i sum_k E_ik ] ------------
         // P_k E_ki = sigma0_k . W0c^T (eps . E_ik), eps = (-,-,+,+,-), so H needs S[c][fd] = sum_{k!=i} sigma0_k[c] E_ik[fd] for
         // the 6 non-zero entries fd of E.  Four of them are cos/sin of theta_i - theta_k and SEPARATE:
@@ -713,6 +972,7 @@ wsweep_kernel(const SweepParams p) {
         }
         __syncwarp();
 
+        PROF_MARK(3);
         // ---------------- Jacobian-side per-row contractions (FP32), rolled over groups of 4 input channels ----
         //   WfS[c][a] = Wf[c][a] sigma1_i[c];  R = WfS W1c^T, T = WfS W1b^T, M = Wf^T + WfS W1a^T, Q = (M . sigma0) W0c^T
         float Q[2][5];
@@ -760,16 +1020,93 @@ wsweep_kernel(const SweepParams p) {
                     }
                 }
                 if (rv) {
+#if CGBW_UFORM
+                    float* sc = sScr + lane * 68 + 8 * e4;       // [(R0,R1) x 16 | (T0,T1) x 16]: pairs over the two rows of the block
+                    *reinterpret_cast<float4*>(sc) = make_float4(r0v[0], r1v[0], r0v[1], r1v[1]);
+                    *reinterpret_cast<float4*>(sc + 4) = make_float4(r0v[2], r1v[2], r0v[3], r1v[3]);
+                    *reinterpret_cast<float4*>(sc + 32) = make_float4(t0v[0], t1v[0], t0v[1], t1v[1]);
+                    *reinterpret_cast<float4*>(sc + 36) = make_float4(t0v[2], t1v[2], t0v[3], t1v[3]);
+#else
                     float* sc = sScr + lane * 68 + 4 * e4;       // [R0 | R1 | T0 | T1] x 16
                     *reinterpret_cast<float4*>(sc) = make_float4(r0v[0], r0v[1], r0v[2], r0v[3]);
                     *reinterpret_cast<float4*>(sc + 16) = make_float4(r1v[0], r1v[1], r1v[2], r1v[3]);
                     *reinterpret_cast<float4*>(sc + 32) = make_float4(t0v[0], t0v[1], t0v[2], t0v[3]);
                     *reinterpret_cast<float4*>(sc + 48) = make_float4(t1v[0], t1v[1], t1v[2], t1v[3]);
+#endif
                 }
             }
         }
 
+        PROF_MARK(4);
         // ---------------- pass 2 + 3: Jacobian blocks  J_ik = Q_i E_ik + R_i F_ik + T_i H_k  -> staging -----------
+#if CGBW_UFORM
+        // R_i F_ik = R_i diag(sigma'_ik) Wt^T E_ik: the 2x5 matrix  U_ik = Q_i + sum_c (sigma'_c R_i[:,c]) Wt[:,c]^T  is accumulated
+        // over the channels (5 packed FMAs per channel on the pair of block rows) and contracted with the 6 non-zeros of E_ik
+        // ONCE per pair, instead of forming Wt^T E_ik per channel (10 -> 6 instructions per pair-channel).
+        {
+            float2 R2[16], T2[16], Q2[5];
+            __syncwarp();                    // padding lanes (>= N) mirror row N-1, written by lane N-1 just above
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float* sc = sScr + kself * 68 + 8 * c4;
+                const float4 a0 = *reinterpret_cast<const float4*>(sc), a1 = *reinterpret_cast<const float4*>(sc + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sc + 32), b1 = *reinterpret_cast<const float4*>(sc + 36);
+                R2[4 * c4] = make_float2(a0.x, a0.y); R2[4 * c4 + 1] = make_float2(a0.z, a0.w);
+                R2[4 * c4 + 2] = make_float2(a1.x, a1.y); R2[4 * c4 + 3] = make_float2(a1.z, a1.w);
+                T2[4 * c4] = make_float2(b0.x, b0.y); T2[4 * c4 + 1] = make_float2(b0.z, b0.w);
+                T2[4 * c4 + 2] = make_float2(b1.x, b1.y); T2[4 * c4 + 3] = make_float2(b1.z, b1.w);
+            }
+#pragma unroll
+            for (int f = 0; f < 5; ++f) Q2[f] = make_float2(Q[0][f], Q[1][f]);
+            __syncwarp();                    // all R|T rows are in registers before the J blocks overwrite the region
+            float2 rsx = make_float2(0.f, 0.f), rsy = make_float2(0.f, 0.f);
+            float4 pn = sPos[0];
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                const float4 pj = pn;
+                pn = sPos[k + 1 < N ? k + 1 : k];
+                if (k != kself) {
+                    const WPairFeat f = wpair_features(pos, npc, pj);
+                    const float i4d = 0.25f * rsqrt_approx(f.d2);
+                    // E_ik = (1/n) d t0_ik / d x_k   (5x2, 6 non-zeros)
+                    const float2 e01 = __fmul2_rn(f.s, make_float2(alpha, alpha)), e23 = __fmul2_rn(f.c, make_float2(-alpha, -alpha));
+                    const float2 e4 = __fmul2_rn(e01, make_float2(-i4d, -i4d));
+                    const float d = f.d2 * (4.f * i4d);
+                    float2 U[5];
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) U[g] = Q2[g];
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) {
+                        const int c = 2 * c2;
+                        const float2 a2 = ffma2s(d, make_float2(cW.wt[4][c], cW.wt[4][c + 1]),
+                                          ffma2s(f.s.y, make_float2(cW.wt[3][c], cW.wt[3][c + 1]),
+                                          ffma2s(f.s.x, make_float2(cW.wt[2][c], cW.wt[2][c + 1]),
+                                          ffma2s(f.c.y, make_float2(cW.wt[1][c], cW.wt[1][c + 1]),
+                                          ffma2s(f.c.x, make_float2(cW.wt[0][c], cW.wt[0][c + 1]), make_float2(cW.bt[c], cW.bt[c + 1]))))));
+                        const float sg0 = sigmoid2(a2.x), sg1 = sigmoid2(a2.y);
+                        const float2 sr0 = __fmul2_rn(R2[c], make_float2(sg0, sg0)), sr1 = __fmul2_rn(R2[c + 1], make_float2(sg1, sg1));
+#pragma unroll
+                        for (int g = 0; g < 5; ++g) U[g] = ffma2s(cW.wt[g][c + 1], sr1, ffma2s(cW.wt[g][c], sr0, U[g]));
+                    }
+                    // J_ik (rows a = 0, 1 packed): column x from features 0, 2, 4, column y from 1, 3, 4
+                    float2 jx = ffma2s(e01.x, U[0], ffma2s(e23.x, U[2], __fmul2_rn(U[4], make_float2(e4.x, e4.x))));
+                    float2 jy = ffma2s(e01.y, U[1], ffma2s(e23.y, U[3], __fmul2_rn(U[4], make_float2(e4.y, e4.y))));
+                    // mean-field coupling through hbar:  T_i H_k
+                    const float4* hk = reinterpret_cast<const float4*>(sH + k * 32);
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) {
+                        const float4 hv = hk[c2];                  // (Hx, Hy)[2 c2], (Hx, Hy)[2 c2 + 1]
+                        jx = ffma2s(hv.x, T2[2 * c2], ffma2s(hv.z, T2[2 * c2 + 1], jx));
+                        jy = ffma2s(hv.y, T2[2 * c2], ffma2s(hv.w, T2[2 * c2 + 1], jy));
+                    }
+                    if (rv) sJ[lane * PB + k] = make_float4(jx.x, jy.x, jx.y, jy.y);
+                    rsx = __fadd2_rn(rsx, jx); rsy = __fadd2_rn(rsy, jy);
+                }
+            }
+            // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
+            if (rv) sJ[lane * PB + lane] = make_float4(1.f - rsx.x, -rsy.x, -rsx.y, 1.f - rsy.y);
+        }
+#else
         {
             float R[2][16], T[2][16];
             __syncwarp();                    // padding lanes (>= N) mirror row N-1, written by lane N-1 just above
@@ -847,6 +1184,7 @@ wsweep_kernel(const SweepParams p) {
             // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
             if (rv) sJ[lane * PB + lane] = make_float4(1.f - rs0, -rs1, -rs2, 1.f - rs3);
         }
+#endif
         __syncwarp();
         if (p.out_jac && step == 0) {
             float* oj = p.out_jac + (size_t)b * (2 * N) * (2 * N);
@@ -857,6 +1195,7 @@ wsweep_kernel(const SweepParams p) {
             }
         }
 
+        PROF_MARK(5);
         // ---------------- Jacobian LU: unpivoted 2x2-block LU, register-resident, rolled (shift-left) --------------
         // Step k: every row eliminates the active block column (register 0) with the published pivot line k and
         // -P_kk^{-1}, writing the updated block j into register j-1.  Right after the first update the new diagonal
@@ -943,153 +1282,151 @@ wsweep_kernel(const SweepParams p) {
         }
         __syncwarp();
 
-        // ---------------- Slater matrix in float64: D_rj = exp(2 pi i m_j . w_r), w = u + dz/L --------------------
-        // (src/slater.py:14-17; the twist and any common displacement are pure row/column phases and drop out of
-        // |det|).  Lane r builds row r from per-particle power tables X_r^m, Y_r^m, m = 0..mmax (one sincospi per
-        // coordinate); for very large |m| the entries are computed directly and staged through shared memory.
-        double aD;
-        {
-            double2 Dr[N];
-            const double wx = fma(dzx, invL, ux), wy = fma(dzy, invL, uy);
-            if (mmax <= L_::MMAX_TAB) {
-                const int PT = (2 * (mmax + 1)) | 1;
-                double2* tb = sPt + kself * PT;
-                if (rv) {
+        PROF_MARK(6);
+        // ---------------- Slater determinant: D_rj = exp(2 pi i m_j . w_r), w = u + dz/L  (src/slater.py:14-19) ---------------
+        // The twist and any common displacement are pure row/column phases and drop out of |det|.  Lane r builds row r from
+        // per-particle power tables X_r^m, Y_r^m, m = 0..mmax (one float64 sincospi per coordinate, float64 recurrence).
+        // Fast path: the tables are rounded to FP32 and the matrix is factored by a partially pivoted complex FP32 LU
+        // (register-resident, shift-left, implicit row exchange).  An a-posteriori bound of its rounding error,
+        //   err^2 ~ eps^2 sum_k k / |u_kk|^2   (k accumulated products in pivot k, amplified by 1 / |pivot|),
+        // is accumulated on the fly; evaluations that exceed the budget (near-singular D: small pivots) or that use
+        // wave vectors beyond the tables are redone by the float64 LU (slater_logdet_f64, same tables in float64).
+        double aD = 0.0;
+        const double wx = fma(dzx, invL, ux), wy = fma(dzy, invL, uy);
+        bool need64 = p.force_f64_slater != 0 || mmax > L_::MMAX_TAB;
+        if (!need64) {
+            const int PT = (2 * (mmax + 1)) | 1;
+            float2* const sPf = reinterpret_cast<float2*>(sm + L_::o_J);
+            float2* const tb = sPf + kself * PT;
+            if (rv) {
 #pragma unroll 1
-                    for (int comp = 0; comp < 2; ++comp) {
-                        const double wv = comp ? wy : wx;
-                        double sn, cs;
-                        sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
-                        double2* t = tb + comp * (mmax + 1);
-                        double2 pw = make_double2(1.0, 0.0);
-                        t[0] = pw;
-                        for (int m = 1; m <= mmax; ++m) {
-                            pw = make_double2(pw.x * cs - pw.y * sn, pw.x * sn + pw.y * cs);
-                            t[m] = pw;
-                        }
+                for (int comp = 0; comp < 2; ++comp) {
+                    const double wv = comp ? wy : wx;
+                    double sn, cs;
+                    sincospi(2.0 * (wv - rint(wv)), &sn, &cs);
+                    float2* t = tb + comp * (mmax + 1);
+                    double2 pw = make_double2(1.0, 0.0);
+                    t[0] = make_float2(1.f, 0.f);
+                    for (int m = 1; m <= mmax; ++m) {
+                        pw = make_double2(pw.x * cs - pw.y * sn, pw.x * sn + pw.y * cs);
+                        t[m] = make_float2((float)pw.x, (float)pw.y);
                     }
                 }
-                __syncwarp();
-                const double2* ty = tb + (mmax + 1);
+            }
+            __syncwarp();
+            float2 Dr[N];
+            {
+                const float2* ty = tb + (mmax + 1);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const int2 mk = sK[j];
-                    double2 X = tb[abs(mk.x)], Y = ty[abs(mk.y)];
+                    float2 X = tb[abs(mk.x)], Y = ty[abs(mk.y)];
                     X.y = mk.x < 0 ? -X.y : X.y;
                     Y.y = mk.y < 0 ? -Y.y : Y.y;
-                    Dr[j] = make_double2(X.x * Y.x - X.y * Y.y, X.x * Y.y + X.y * Y.x);
+                    Dr[j] = make_float2(fmaf(X.x, Y.x, -X.y * Y.y), fmaf(X.x, Y.y, X.y * Y.x));
                 }
-            } else {
-                double2* row = sPt + kself * PB;
-#pragma unroll 1
-                for (int j = 0; j < N; ++j) {
-                    const int2 mk = sK[j];
-                    double ph = fma((double)mk.x, wx, (double)mk.y * wy);
-                    ph -= rint(ph);
-                    double sn, cs;
-                    sincospi(2.0 * ph, &sn, &cs);
-                    if (rv) row[j] = make_double2(cs, sn);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < N; ++j) Dr[j] = row[j];
             }
             __syncwarp();     // H region (lines) free, tables read
-
-            // ---------------- Slater LU: partially pivoted, implicit row exchange, register-resident, rolled ---------
-            // Same shift-left scheme: the active column is register 0.  After its first update every unfinished
-            // row offers its new register 0; one REDUX picks the next pivot row, which publishes 1/pivot (the
-            // reciprocal chain overlaps the remaining updates) and then its row.  Finished rows compute garbage.
+            PROF_MARK(7);
+            // ---- complex FP32 LU.  Step k: every unfinished row offers |entry|^2 of the active column (register 0); ONE
+            // REDUX picks the pivot row.  Every lane has already computed the reciprocal of ITS OWN candidate (no
+            // divergence, and the MUFU runs beside the REDUX instead of after it), so the winner's 1/pivot arrives by two
+            // shuffles.  The update  v += l p  is two packed FMAs per entry:  (vx, vy) += px (lx, ly) + py (-ly, lx);
+            // the pivot line travels through a double-buffered shared-memory line as plain (x, y) pairs, loaded one
+            // chunk of 8 entries ahead of its use.
+            constexpr int LP = (N + 18) & ~1;                   // float2 slots per line buffer: entry j sits in slot j + 1 (entry 1 is
+                                                                // 16-byte aligned), + prefetch padding
+            float2* const fline0 = reinterpret_cast<float2*>(sm + L_::o_H);     // [2][LP]
             bool done = !rv, singular = false;
-            double mypn = 1.0;
-            constexpr int LP = N + 8;
-            double2* const dline0 = reinterpret_cast<double2*>(sm + L_::o_H);    // [2][LP]
-            auto offer = [&](const double2 e) -> unsigned {
-                const float mag = (float)(fabs(e.x) + fabs(e.y));
-                const unsigned key = done ? 0u : ((__float_as_uint(mag) & ~0x1Fu) | (unsigned)lane);
+            float mypn = 1.f, myerr = 0.f;
+            unsigned chk = 0u;
+            float pn, rinv;
+            float2 own;
+            auto offer = [&](const float2 e) -> unsigned {
+                pn = fmaf(e.x, e.x, e.y * e.y);
+                rinv = rcp_approx(pn);
+                own = make_float2(e.x * rinv, -e.y * rinv);     // 1 / e
+                const unsigned key = done ? 0u : ((__float_as_uint(pn) & ~0x1Fu) | (unsigned)lane);
                 return __reduce_max_sync(FULL, key);
             };
-            // 1/pivot, computed by EVERY lane from the shuffled pivot (no divergent branch, no shared-memory round trip):
-            // FP32 seed of 1/|e|^2 from the FP32-rounded entry + one float64 Newton step (2^-23 squared)
-            double pn = 1.0;
-            auto pivot_inv = [&](const double2 e) -> double2 {
-                pn = fma(e.x, e.x, e.y * e.y);
-                const float ex = (float)e.x, ey = (float)e.y;
-                const double r0 = (double)rcp_approx(fmaf(ex, ex, ey * ey));
-                const double ip = r0 * (2.0 - pn * r0);
-                return make_double2(e.x * ip, -e.y * ip);
-            };
             unsigned wk = offer(Dr[0]);
-            double2 iv = pivot_inv(shfl2dw(Dr[0], (int)(wk & 31u)));
+            float2 iv = make_float2(__shfl_sync(FULL, own.x, (int)(wk & 31u)), __shfl_sync(FULL, own.y, (int)(wk & 31u)));
             bool win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
             if (win) {
-                mypn = pn;
+                mypn = pn; myerr = rinv;
 #pragma unroll
-                for (int j = 1; j < N; ++j) dline0[j] = Dr[j];
+                for (int j = 1; j < N; ++j) fline0[j + 1] = Dr[j];
             }
             __syncwarp();
 #pragma unroll 1
             for (int k = 0; k < N; ++k) {
-                const double2* cur = dline0 + (k & 1) * LP;
-                double2* nxt = dline0 + ((k + 1) & 1) * LP;
-                const unsigned dcur32 = (unsigned)__cvta_generic_to_shared(cur);
+                const float2* cur = fline0 + (k & 1) * LP;
+                float2* nxt = fline0 + ((k + 1) & 1) * LP;
+                const unsigned cur32 = (unsigned)__cvta_generic_to_shared(cur);
                 const int lim = N - 1 - k;
                 singular |= (wk >> 5) == 0u;
                 done |= win;
                 if (lim == 0) break;
-                const double2 c = Dr[0];
-                const double lx = -(c.x * iv.x - c.y * iv.y);               // l = -c / pivot
-                const double ly = -(c.x * iv.y + c.y * iv.x);
-                double2 pq[4] = {cur[1], cur[2], cur[3], cur[4]};
+                const float2 c = Dr[0];
+                const float2 L1 = make_float2(-(c.x * iv.x - c.y * iv.y), -(c.x * iv.y + c.y * iv.x));   // l = -c / pivot
+                const float2 L2 = make_float2(-L1.y, L1.x);
+                float4 pq[4];
 #pragma unroll
-                for (int j0 = 1; j0 < N; j0 += 4) {
-                    if (j0 > lim) break;
-                    double2 nq[4];
+                for (int t = 0; t < 4; ++t) pq[t] = lds_pinned_f4(cur32 + 16u + 16u * (unsigned)t);       // entries 1..8
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-#if CGBW_PIN_LDS
-                        nq[t] = lds_pinned_d2(dcur32 + 16u * (unsigned)(j0 + 4 + t));
-#else
-                        nq[t] = cur[j0 + 4 + t];
-#endif
+                for (int j0 = 1; j0 < N; j0 += 8) {
+                    if (j0 > lim) break;                          // warp-uniform; at most seven dead entries of work
+                    float4 nq[4];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)                               // independent first halves (written straight to the
-                        if (j0 + t < N) {                                     // shifted slot): covers the DFMA latency
-                            const double2 o = Dr[j0 + t];
-                            Dr[j0 + t - 1] = make_double2(fma(-ly, pq[t].y, o.x), fma(ly, pq[t].x, o.y));
-                        }
+                    for (int t = 0; t < 4; ++t) nq[t] = lds_pinned_f4(cur32 + 16u + 16u * (unsigned)(((j0 - 1) >> 1) + 4 + t));
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
+                    for (int t = 0; t < 8; ++t) {
                         const int j = j0 + t;
                         if (j < N) {
-                            double2 v = Dr[j - 1];
-                            v.x = fma(lx, pq[t].x, v.x);
-                            v.y = fma(lx, pq[t].y, v.y);
+                            const float px = (t & 1) ? pq[t >> 1].z : pq[t >> 1].x, py = (t & 1) ? pq[t >> 1].w : pq[t >> 1].y;
+                            const float2 v = ffma2s(px, L1, ffma2s(py, L2, Dr[j]));
                             Dr[j - 1] = v;
                             if (j == 1) {
                                 wk = offer(v);
-                                iv = pivot_inv(shfl2dw(v, (int)(wk & 31u)));
+                                iv = make_float2(__shfl_sync(FULL, own.x, (int)(wk & 31u)), __shfl_sync(FULL, own.y, (int)(wk & 31u)));
                                 win = !done && lane == (int)(wk & 31u) && (wk >> 5) != 0u;
-                                if (win) mypn = pn;
+                                if (win) { mypn = pn; myerr = (float)(k + 2) * rinv; }
                             }
                         }
                     }
+                    if (win) {                                    // the next pivot row publishes this chunk of its row
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const int j = j0 + t;
+                            if (j >= 2 && j < N) nxt[j] = Dr[j - 1];          // entry j - 1 of the next line
+                        }
+                    }
+                    chk ^= __float_as_uint(nq[3].w);              // a use inside this block keeps the prefetch where it is written
 #pragma unroll
                     for (int t = 0; t < 4; ++t) pq[t] = nq[t];
                 }
-                if (win) {
-#pragma unroll
-                    for (int j = 1; j < N - 1; ++j) {
-                        if ((j & 3) == 1 && j >= lim) break;
-                        nxt[j] = Dr[j];
-                    }
-                }
                 __syncwarp();
             }
-            aD = (rv && mypn != 1.0) ? 0.5 * log(mypn) : 0.0;
+            // error bound of the FP32 factorisation (see above) and the decision to redo in float64
+            float es = myerr;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
+#ifdef CGBW_DIAG_ERRSUM                    // calibration build: never fall back on the indicator, export it instead
+            need64 = singular || chk == 0x7fc0dead;
+#else
+            need64 = singular || !(es < p.slater32_errsum_max) || chk == 0x7fc0dead;    // (chk: never true, keeps the prefetch alive)
+#endif
+            aD = (rv && mypn != 1.f) ? 0.5 * log((double)mypn) : 0.0;
             aD = warp_sum_f64(aD);
-            if (singular) aD = -INFINITY;             // slogdet of a singular matrix: log|det| = -inf (slater.py:18)
+#ifdef CGBW_DIAG_ERRSUM
+            aJ_diag = (double)es;
+#endif
         }
+        if (need64) {
+            aD = slater_logdet_f64<N>(sm, sK, lane, kself, rv, mmax, wx, wy);
+            if (lane == 0 && p.fallback_counter) atomicAdd(p.fallback_counter + 1, 1ull);
+        }
+        PROF_MARK(8);
         aJ = lacc_per_lane ? warp_sum_f64((double)lacc * 0.693147180559945309417)
                            : (double)lacc * 0.693147180559945309417;
         ldD = aD - nlogL;
@@ -1139,6 +1476,7 @@ wsweep_kernel(const SweepParams p) {
                     if (lane == 0) {
                         if (p.out_logp) p.out_logp[b] = sp_logp;
                         if (p.out_naccept) p.out_naccept[b] = sp_nacc;
+                        if (p.out_stats && p.mc_steps > 0) atomicAdd(p.out_stats + CGB_STATS_NACCEPT, (double)sp_nacc);
                     }
                 }
                 sp_b += gridDim.x;
@@ -1149,6 +1487,9 @@ wsweep_kernel(const SweepParams p) {
         int acc = 1;
         if (step == 0) {
             logp_cur = lp;
+#ifdef CGBW_DIAG_ERRSUM
+            aJ = aJ_diag;              // calibration build: the FP32 Slater LU's error indicator instead of log|det J|
+#endif
             if (p.out_parts && lane == 0) { p.out_parts[2 * (size_t)b] = ldD; p.out_parts[2 * (size_t)b + 1] = aJ; }
         } else {
             const double u = uniform_of(b, step);
@@ -1178,6 +1519,7 @@ wsweep_kernel(const SweepParams p) {
             if (last) {
                 if (p.out_logp) p.out_logp[b] = logp_cur;
                 if (p.out_naccept) p.out_naccept[b] = na;
+                if (p.out_stats && p.mc_steps > 0) atomicAdd(p.out_stats + CGB_STATS_NACCEPT, (double)na);   // integers: exact, order-free
             } else {
                 p.ws_logp[b] = logp_cur;
                 p.ws_nacc[b] = na;
@@ -1194,51 +1536,61 @@ wsweep_kernel(const SweepParams p) {
                 st_release_u64(slot, ((unsigned long long)(unsigned)(t + 1ull) << 32) | (unsigned long long)(unsigned)b);
             }
         }
+        PROF_MARK(9);
         }
     }
+#if CGBW_PROF
+    if (lane == 0 && p.prof)
+        for (int i = 0; i < 12; ++i) atomicAdd(p.prof + i, s_prof[threadIdx.x >> 5][i]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
 // instantiated shapes: the closed shells of the 2D plane-wave lattice up to one warp (the reference's runs use 13, 29)
 bool wsweep_supported(int n) { return n == 9 || n == 13 || n == 21 || n == 25 || n == 29; }
 
+// launch configuration per (device, instantiation): function attribute + occupancy are queried once, the steady-state
+// call is the launch alone
+struct WLaunchCfg { int dev = -1; int wpc = 0; int occ = 0; size_t smem = 0; };
+
 template <int N>
 static int launch_wn(const SweepParams& p, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static thread_local int sms_cache[2] = {-1, 0};
+    if (sms_cache[0] != dev) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); sms_cache[0] = dev; sms_cache[1] = sms; }
+    sms = sms_cache[1];
+    auto config = [&](auto kern, const int nw, WLaunchCfg& c) -> int {
+        if (c.dev == dev && c.wpc == nw) return 0;
+        const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * nw;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem);
+        c.dev = dev; c.wpc = nw; c.occ = occ < 1 ? 1 : occ; c.smem = smem;
+        return 0;
+    };
     if (p.spec) {          // speculative mode: one CTA of 8 (B <= #SMs) or 4 warps per walker, persistent over the sweep
-        auto go = [&](auto kern, const int nw) -> int {
-            const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * nw;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            int occ = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem);
-            if (occ < 1) occ = 1;
-            long long grid = (long long)sms * occ;
+        auto go = [&](auto kern, const int nw, WLaunchCfg& c) -> int {
+            if (const int rc = config(kern, nw, c)) return rc;
+            long long grid = (long long)sms * c.occ;
             if (grid > (long long)p.B) grid = p.B;
-            kern<<<(int)grid, nw * 32, smem, st>>>(p);
+            kern<<<(int)grid, nw * 32, c.smem, st>>>(p);
             return (int)cudaGetLastError();
         };
-        return p.spec == 8 ? go(wsweep_kernel<N, 8>, 8) : go(wsweep_kernel<N, 4>, 4);
+        static thread_local WLaunchCfg c8, c4;
+        return p.spec == 8 ? go(wsweep_kernel<N, 8>, 8, c8) : go(wsweep_kernel<N, 4>, 4, c4);
     }
     // warps per CTA: 4 when the batch fills the machine, fewer for small batches so the walkers spread over all SMs
     int wpc = CGBW_WPC;
     while (wpc > 1 && (long long)p.B < (long long)sms * 3 * wpc) wpc >>= 1;
-    if (const char* s = getenv("CGB_W_WPC")) { const int v = atoi(s); if (v >= 1 && v <= CGBW_WPC) wpc = v; }   // tuning knobs
-    long long max_grid = 1ll << 40;
-    if (const char* s = getenv("CGB_W_GRID")) { const long long v = atoll(s); if (v >= 1) max_grid = v; }
-    const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * wpc;
-    cudaError_t e = cudaFuncSetAttribute(wsweep_kernel<N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsweep_kernel<N, 0>, wpc * 32, smem);
-    if (occ < 1) occ = 1;
-    long long grid = (long long)sms * occ;
+    static thread_local WLaunchCfg cq[CGBW_WPC + 1];
+    WLaunchCfg& c = cq[wpc];
+    if (const int rc = config(wsweep_kernel<N, 0>, wpc, c)) return rc;
+    long long grid = (long long)sms * c.occ;
     const long long need = ((long long)p.B + wpc - 1) / wpc;      // never more warps than walkers
     if (grid > need) grid = need;
-    if (grid > max_grid) grid = max_grid;
-    wsweep_kernel<N, 0><<<(int)grid, wpc * 32, smem, st>>>(p);
+    wsweep_kernel<N, 0><<<(int)grid, wpc * 32, c.smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -1255,32 +1607,55 @@ int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
     if (!wsweep_supported(p.n)) return CGB_E_UNSUPPORTED;
     if ((unsigned long long)p.B * (unsigned long long)(p.mc_steps + 2) >= (1ull << 31)) return CGB_E_UNSUPPORTED;
     if (p.wconst != wconst_staging) return CGB_E_BADARG;
-    // the constant bank is per device: make sure it is the stream's device that gets refreshed and launched on
+    // the constant bank is per device: make sure it is the stream's device that gets refreshed and launched on (not asked of a
+    // stream under graph capture: only launches and memcpy nodes are issued on those)
     int cur_dev = 0, st_dev = -1;
     cudaGetDevice(&cur_dev);
-    if (st != nullptr && cudaStreamGetDevice(st, &st_dev) == cudaSuccess && st_dev != cur_dev) return CGB_E_BADARG;
-    prep_wconst_kernel<<<1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging));
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap_st) != cudaSuccess) { cap_st = cudaStreamCaptureStatusNone; (void)cudaGetLastError(); }
+    if (cap_st == cudaStreamCaptureStatusNone && st != nullptr) {
+        if (cudaStreamGetDevice(st, &st_dev) == cudaSuccess) { if (st_dev != cur_dev) return CGB_E_BADARG; }
+        else (void)cudaGetLastError();
+    }
+    const unsigned cap = p.spec ? 0u : (unsigned)p.qcap;
+    wsweep_prologue_kernel<<<cap ? (cap + 255) / 256 : 1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging), p.queue,
+                                                                       cap, (unsigned)p.B, p.qctr, p.done, p.out_stats,
+                                                                       (double)p.B * (double)p.mc_steps,
+                                                                       const_cast<uint32_t*>(p.key_dev), p.advance_key);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    // constant bank refresh, stream-ordered (device-to-device): calls on one stream are serialised by the stream;
-    // concurrent sweeps with DIFFERENT parameters on different streams of one device must be serialised by the caller.
+    // Constant bank refresh, stream-ordered (device-to-device).  The block is per DEVICE: the refresh must not overtake a
+    // sweep of another stream that still reads the previous content.  One event per device marks the last reader; a call on a
+    // different stream waits for it before refreshing (sweeps of different streams are serialised on the device, each sees its
+    // own parameters).  A stream under graph capture cannot take or give that dependency (include/cgb200.h).
+    static std::mutex guard_mu;
+    static struct { cudaEvent_t ev; cudaStream_t last; bool have; } guard[64] = {};
+    const std::lock_guard<std::mutex> lock(guard_mu);
+    const bool guarded = cap_st == cudaStreamCaptureStatusNone && cur_dev >= 0 && cur_dev < 64;
+    if (guarded && guard[cur_dev].have && guard[cur_dev].last != st) {
+        e = cudaStreamWaitEvent(st, guard[cur_dev].ev, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
     e = cudaMemcpyToSymbolAsync(cW, wconst_staging, sizeof(WConst), 0, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return (int)e;
-    if (!p.spec) {
-        wqueue_init_kernel<<<(p.qcap + 255) / 256, 256, 0, st>>>(p.queue, (unsigned)p.qcap, (unsigned)p.B, p.qctr);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-        e = cudaMemsetAsync(p.done, 0, sizeof(int) * (size_t)p.B, st);
-        if (e != cudaSuccess) return (int)e;
-    }
+    int rc;
     switch (p.n) {
-        case 9: return launch_wn<9>(p, st);
-        case 13: return launch_wn<13>(p, st);
-        case 21: return launch_wn<21>(p, st);
-        case 25: return launch_wn<25>(p, st);
-        case 29: return launch_wn<29>(p, st);
-        default: return CGB_E_UNSUPPORTED;
+        case 9: rc = launch_wn<9>(p, st); break;
+        case 13: rc = launch_wn<13>(p, st); break;
+        case 21: rc = launch_wn<21>(p, st); break;
+        case 25: rc = launch_wn<25>(p, st); break;
+        case 29: rc = launch_wn<29>(p, st); break;
+        default: rc = CGB_E_UNSUPPORTED;
     }
+    if (guarded && rc == 0) {
+        if (!guard[cur_dev].have) {
+            if (cudaEventCreateWithFlags(&guard[cur_dev].ev, cudaEventDisableTiming) != cudaSuccess) return rc;
+            guard[cur_dev].have = true;
+        }
+        cudaEventRecord(guard[cur_dev].ev, st);
+        guard[cur_dev].last = st;
+    }
+    return rc;
 }
 
 }  // namespace cgb

@@ -16,12 +16,18 @@
  *
  * Conventions (all launchers):
  *   - asynchronous on the caller's stream (`stream` is a cudaStream_t passed as void*), device pointers
- *     only, no allocation, no synchronisation, no host-side mutable state (one call per stream at a time
- *     per workspace); the caller owns every buffer; workspace size comes from the *_workspace_bytes(B, n)
- *     query and grows with the batch (ready queue + per-walker scheduler state of the sweep kernel).
- *     The warp-per-walker sweep kernel (n = 9, 13, 21, 25, 29) keeps its weights in a per-device __constant__ block that every call
- *     refreshes stream-ordered: sweeps with DIFFERENT parameters must not overlap on different streams of
- *     one device (same parameters, or one stream per device as under jax.pmap, is always fine).
+ *     only, no allocation, no synchronisation (one call per stream at a time per workspace); the caller owns
+ *     every buffer; workspace size comes from the *_workspace_bytes(B, n) query and grows with the batch
+ *     (ready queue + per-walker scheduler state of the sweep kernel).  No environment variable is read on
+ *     the launch path: kernel choice and debug switches are the per-call `flags` argument.
+ *     The warp-per-walker sweep kernel (n = 9, 13, 21, 25, 29) reads its weights as constant-bank operands
+ *     from a per-device __constant__ block that every call refreshes stream-ordered.  Calls on DIFFERENT
+ *     streams of one device are made safe by the library itself: it keeps one event per device ("last
+ *     kernel that read the block") and makes the refresh of the next call wait for it, i.e. such sweeps are
+ *     serialised on the device (they would each fill the GPU anyway) and every call sees its own parameters.
+ *     The one exception is a stream that is being CAPTURED into a CUDA graph: no cross-stream dependency can
+ *     be added there, so graphs holding sweeps with different parameters must not be replayed concurrently
+ *     on one device.  This per-device event (mutex-protected) is the only host-side state of the library.
  *   - I/O buffers are float64 (the reference runs with jax_enable_x64, main.py:2-3); internal arithmetic is
  *     FP32 with float64 range reduction / log-det accumulation / Metropolis test.
  *   - return 0 on success, CGB_E_* (<0) for bad arguments / unsupported shapes, or the positive
@@ -46,7 +52,33 @@ extern "C" {
 
 #define CGB_NPARAMS        1074  /* flat flow parameter vector, see cgb_pack order below */
 #define CGB_MAX_N            64
-#define CGB_ABI_VERSION       1
+#define CGB_ABI_VERSION       2
+
+/* per-call flags (logp / sweep launchers).  Bits 0-3: kernel choice, for A/B measurements and tests only -- results do not
+ * depend on it (same noise/uniform streams, same decisions in the same order); 0 lets the library choose. */
+#define CGB_KERNEL_AUTO       0u
+#define CGB_KERNEL_CTA        1u   /* CTA-per-walker kernel, sequential chains */
+#define CGB_KERNEL_CTA4       2u   /* ... clusters of 4 CTAs per walker (speculative) */
+#define CGB_KERNEL_CTA8       3u   /* ... clusters of 8 */
+#define CGB_KERNEL_WARP       4u   /* warp-per-walker kernel with the ready queue (n = 9, 13, 21, 25, 29) */
+#define CGB_KERNEL_SPEC4      5u   /* ... speculative, 4 warps per walker */
+#define CGB_KERNEL_SPEC8      6u   /* ... speculative, 8 warps per walker */
+#define CGB_KERNEL_MASK      15u
+#define CGB_FLAG_FORCE_PIVOT  0x100u   /* debug: Jacobian log-det by the partially pivoted fallback LU */
+#define CGB_FLAG_ADVANCE_KEY  0x200u   /* sweep: key_dev <- key_dev + golden-ratio increment BEFORE it is used (see below) */
+#define CGB_FLAG_FORCE_F64_SLATER 0x400u   /* debug: Slater log-det by the float64 LU even where the FP32 LU passes its monitor */
+
+/* Statistics vector of one sampling step (device, CGB_STATS_LEN float64): what the reference's pmean sites reduce
+ * (src/MCMC.py:38-39 accept rate; the V_mean / V2_mean entries of src/VMC.py:46-53).  One all-reduce (sum) of entries 0..4
+ * over the ranks gives the global statistics.  The sweep launcher zeroes the vector and fills [0], [1]; the Ewald launcher
+ * fills [2], [3], [4] (deterministically: one fixed-order reduction by the last CTA to finish); [7] is scratch and must be
+ * zero when the Ewald launcher is called on a vector the sweep launcher has not initialised. */
+#define CGB_STATS_LEN          8
+#define CGB_STATS_NACCEPT      0   /* sum over walkers of accepted moves */
+#define CGB_STATS_NPROPOSED    1   /* B * mc_steps */
+#define CGB_STATS_SUM_V        2   /* sum_b V_b  (without Vconst) */
+#define CGB_STATS_SUM_V2       3   /* sum_b V_b^2 */
+#define CGB_STATS_NWALKERS     4   /* B */
 
 /* Flat parameter layout (float64, CGB_NPARAMS entries), haiku module names of src/flow.py:
  *   Wt (5x16)  bt (16)   "fermi_net/~/linear_2"   two-particle layer   src/flow.py:13,46
@@ -84,14 +116,20 @@ int cgb_mcmc_workspace_bytes(int B, int n, size_t* bytes);
 int cgb_logp_f64io(void* stream, const double* x, const int32_t* state_idx, const double* ktable, int M,
                    const double twist[2], const double* params, int B, int n, double L,
                    double* out_logp, double* out_parts, float* out_jac, void* workspace,
-                   size_t workspace_bytes);
+                   size_t workspace_bytes, unsigned flags);
 
 /* ---- Metropolis sweep  (src/MCMC.py:22-40 + src/VMC.py:24) ---------------------------------- */
 /* x_inout (B,n,2) f64 is advanced in place by mc_steps all-electron Gaussian moves (donated buffer,
  * src/VMC.py:11).  Parity mode: noise (mc_steps,B,n,2) f64 ~ N(0,1) and uniforms (mc_steps,B) f64 in
  * [0,1) are supplied by the caller (they replace jax.random.normal/uniform, MCMC.py:26,29).
- * Throughput mode: noise == uniforms == NULL and the kernel draws from Philox4x32-10 keyed by `seed`.
+ * Throughput mode: noise == uniforms == NULL and the kernel draws from Philox4x32-10.  The Philox key is
+ * `seed`, or -- when key_dev != NULL -- the device-resident (2,) uint32 PRNG key the reference carries per
+ * device inside pmap (src/VMC.py:20, src/MCMC.py:24; key[0] << 32 | key[1]), read by the kernel itself: no
+ * host round trip, no recompilation per step.  With CGB_FLAG_ADVANCE_KEY the launcher first replaces the
+ * device key by key + 0x9E3779B97F4A7C15 (mod 2^64) and the sweep uses the new value: a captured CUDA graph
+ * of the step then draws fresh noise on every replay (the analogue of `key, subkey = split(key)`).
  * wrap != 0 applies x -= L*floor(x/L) at the end (VMC.py:24).
+ * out_stats (CGB_STATS_LEN f64, device) or NULL: zeroed, then [0] = accepted moves, [1] = B*mc_steps.
  * Outputs: out_logp (B) f64 final log p per walker; out_naccept (B) int32 accepted moves per walker
  * (accept_rate = sum / (mc_steps*B), MCMC.py:38-39 — the cross-device mean is the caller's psum);
  * out_accept_trace (mc_steps,B) uint8 or NULL; out_logp_trace (mc_steps+1,B) f64 proposal log p
@@ -100,20 +138,20 @@ int cgb_logp_f64io(void* stream, const double* x, const int32_t* state_idx, cons
  * GPU; for small batches (the reference's per-device shards: 256 walkers at n=29, 64 at n=49/57) a
  * speculative mode that evaluates the proposals of the next 2-3 steps of every chain at once on the
  * otherwise idle SMs -- same noise/uniform streams, same decisions in the same order, so the result
- * does not depend on the choice.  Environment override for A/B measurements only:
- * CGB_SWEEP_KERNEL = warp | spec4 | spec8 | cta | cta4 | cta8. */
+ * does not depend on the choice.  `flags`: CGB_KERNEL_* override for A/B measurements. */
 int cgb_mcmc_sweep_f64io(void* stream, double* x_inout, const int32_t* state_idx, const double* ktable,
                          int M, const double twist[2], const double* params, const double* noise,
-                         const double* uniforms, uint64_t seed, int mc_steps, double mc_stddev, double L,
-                         int B, int n, int wrap, double* out_logp, int32_t* out_naccept,
-                         uint8_t* out_accept_trace, double* out_logp_trace, void* workspace,
-                         size_t workspace_bytes);
+                         const double* uniforms, uint64_t seed, uint32_t* key_dev, int mc_steps,
+                         double mc_stddev, double L, int B, int n, int wrap, double* out_logp,
+                         int32_t* out_naccept, uint8_t* out_accept_trace, double* out_logp_trace,
+                         double* out_stats, void* workspace, size_t workspace_bytes, unsigned flags);
 
 /* ---- Ewald energy  (src/potential.py:36-77) ------------------------------------------------- */
 /* x (B,n,2) f64; items (n_items x 4 floats, device) and gmax from cgb_ewald_prepare_host;
- * out_V (B) f64 = 2*rs/L * psi(x/L)   (caller adds Vconst, src/VMC.py:40). */
+ * out_V (B) f64 = 2*rs/L * psi(x/L)   (caller adds Vconst, src/VMC.py:40).
+ * out_stats (CGB_STATS_LEN f64, device) or NULL: [2] = sum V, [3] = sum V^2, [4] = B (see CGB_STATS_*). */
 int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, double rs, double kappa,
-                    const float* items, int n_items, int gmax, double* out_V);
+                    const float* items, int n_items, int gmax, double* out_V, double* out_stats);
 
 /* ---- autoregressive momentum sampler (SURVEY section 8 f/N2: the caller right before the sweep) -------------- */
 /* Replaces `sampler(params_van, key, batch)` and `log_prob(params_van, state_idx)` of
@@ -124,13 +162,14 @@ int cgb_ewald_f64io(void* stream, const double* x, int B, int n, double L, doubl
  * b[16]; mlp/linear w[16][32] b[32]; mlp/linear_1 w[32][16] b[16]} | output_mlp w[16][M] b[M]   (haiku [in][out]).
  * ktable (M,2) f64 device = sp_indices_twist.  n <= 64, n <= M <= 256.
  * sample: gumbel (B,n,M) f64 = the Gumbel noise jax.random.categorical would add to the logits (parity mode), or
- *   NULL -> Philox4x32-10 keyed by (seed; walker, draw, orbital).  out_state_idx (B,n) int32 strictly increasing;
+ *   NULL -> Philox4x32-10 keyed by (seed; walker, draw, orbital); key_dev != NULL: the key is the device-resident
+ *   (2,) uint32 array instead of `seed` (src/VMC.py:20-22).  out_state_idx (B,n) int32 strictly increasing;
  *   out_logprob (B) f64 = log_prob of the drawn states, or NULL; out_logits (B,n,M) f64 masked logits, or NULL.
  * logprob: the same pass with the choices given (sampler.py:40-44). */
 size_t cgb_van_nparams(int M);
 int cgb_van_sample_f64io(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n,
-                         int B, const double* gumbel, uint64_t seed, int32_t* out_state_idx, double* out_logprob,
-                         double* out_logits);
+                         int B, const double* gumbel, uint64_t seed, const uint32_t* key_dev, int32_t* out_state_idx,
+                         double* out_logprob, double* out_logits);
 int cgb_van_logprob_f64io(void* stream, const double* params, size_t nparams, const double* ktable, int M, int n,
                           int B, const int32_t* state_idx, double* out_logprob, double* out_logits);
 
@@ -140,6 +179,14 @@ int cgb_van_logprob_f64io(void* stream, const double* params, size_t nparams, co
  * kind 1: 8 independent ex2.approx chains (8*iters MUFU ops per thread);
  * kind 2: 8 independent DFMA chains (float64). */
 int cgb_microbench(void* stream, int kind, int blocks, int iters, float* out);
+
+/* ---- debug export of the throughput mode's random streams (tests only) ----------------------- */
+/* out_normal (S,B,n,2) f32 / out_uniform (S,B) f64 (either may be NULL): exactly the proposal noise and Metropolis
+ * uniforms the sweep kernels draw for (walker b, step s+1, particle i) under `seed` / `key_dev`.
+ * kat_in (n_kat,6) u32 = Philox counter[4] + key[2], kat_out (n_kat,4) u32 = the raw Philox4x32-10 block (known-answer
+ * vectors of Random123).  All device pointers. */
+int cgb_debug_rng(void* stream, uint64_t seed, const uint32_t* key_dev, int B, int S, int n, float* out_normal,
+                  double* out_uniform, const uint32_t* kat_in, uint32_t* kat_out, int n_kat);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ def test_exports_match_header():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.cgb_abi_version() == 1
+    assert _lib.lib.cgb_abi_version() == 2
 
 
 def test_bad_arguments_return_codes():
@@ -27,12 +27,19 @@ def test_bad_arguments_return_codes():
     tw = (ctypes.c_double * 2)(0.25, 0.25)
     null = ctypes.c_void_p(0)
     one = ctypes.c_void_p(16)      # non-null dummy; never dereferenced because validation fails first
-    assert lib.cgb_logp_f64io(null, null, one, one, 81, tw, one, 4, 13, 6.39, one, null, null, one, 8192) == -1
-    assert lib.cgb_logp_f64io(null, one, one, one, 81, tw, one, 4, 65, 6.39, one, null, null, one, 8192) == -2   # n > 64
-    assert lib.cgb_logp_f64io(null, one, one, one, 81, tw, one, 4, 13, 6.39, one, null, null, null, 0) == -3     # workspace
-    assert lib.cgb_mcmc_sweep_f64io(null, one, one, one, 81, tw, one, one, null, 0, 5, 0.1, 6.39, 4, 13, 1,
-                                    one, one, null, null, one, 8192) == -1                                      # noise w/o uniforms
-    assert lib.cgb_ewald_f64io(null, one, 4, 13, 6.39, 10.0, 10.0, null, 10, 15, one) == -1
+    assert lib.cgb_logp_f64io(null, null, one, one, 81, tw, one, 4, 13, 6.39, one, null, null, one, 8192, 0) == -1
+    assert lib.cgb_logp_f64io(null, one, one, one, 81, tw, one, 4, 65, 6.39, one, null, null, one, 8192, 0) == -2   # n > 64
+    assert lib.cgb_logp_f64io(null, one, one, one, 81, tw, one, 4, 13, 6.39, one, null, null, null, 0, 0) == -3     # workspace
+    assert lib.cgb_logp_f64io(null, one, one, one, 81, tw, one, 4, 13, 6.39, one, null, null, one, 1 << 20, 9) == -1   # kernel id
+    sweep = lambda noise, unif, key, flags: lib.cgb_mcmc_sweep_f64io(
+        null, one, one, one, 81, tw, one, noise, unif, 0, key, 5, 0.1, 6.39, 4, 13, 1, one, one, null, null, null, one, 8192, flags)
+    assert sweep(one, null, null, 0) == -1                               # noise without uniforms
+    assert sweep(null, null, null, _lib.FLAG_ADVANCE_KEY) == -1          # advancing needs a device key
+    assert sweep(null, null, ctypes.c_void_p(18), 0) == -1               # misaligned device key
+    assert sweep(null, null, null, 0) == -3                              # valid arguments, workspace too small for B = 4
+    assert lib.cgb_ewald_f64io(null, one, 4, 13, 6.39, 10.0, 10.0, null, 10, 15, one, null) == -1
+    assert lib.cgb_van_sample_f64io(null, one, 18 * 81 + 4368, one, 81, 13, 4, null, 0, null, null, null, null) == -1
+    assert lib.cgb_debug_rng(null, 0, null, 4, 4, 13, null, null, null, null, 3) == -1
     assert lib.cgb_microbench(null, 7, 1, 1, one) == -1
     assert b"unsupported" in lib.cgb_error_string(-2)
     nb = ctypes.c_size_t()

@@ -24,15 +24,15 @@ def cg():
 
 
 @pytest.fixture(autouse=True, params=["auto", "warp", "cta"])
-def sweep_kernel_choice(request, monkeypatch):
+def sweep_kernel_choice(request, cg):
     """Every test runs three times: with the library's own kernel choice (small batches of the warp-kernel shapes go to
     its speculative mode), with the ready-queue warp-per-walker kernel preferred wherever it has an instance (n = 13,
-    29), and with the CTA-per-walker kernel forced."""
-    if request.param != "auto":
-        monkeypatch.setenv("CGB_SWEEP_KERNEL", request.param)
-    else:
-        monkeypatch.delenv("CGB_SWEEP_KERNEL", raising=False)
-    return request.param
+    29), and with the CTA-per-walker kernel forced.  (The choice is a per-call flag of the C ABI; the host layer's
+    process-wide default is set here and restored afterwards.)"""
+    cg.set_sweep_kernel(None if request.param == "auto" else request.param)
+    yield request.param
+    cg.set_sweep_kernel(None)
+    cg.set_debug(force_pivot=False, force_f64_slater=False)
 
 
 @pytest.fixture(scope="module")
@@ -144,9 +144,9 @@ def test_jacobian_lu_fallback(cg, cases, oracle, monkeypatch):
     logp = cg.make_logp(c["ktable"], c["L"])
     fast = logp(c["x"][:nb], c["params"], c["state_idx"][:nb])
     assert logp.fallback_count() == 0                      # trained flow: J = I + O(0.1), never falls back
-    monkeypatch.setenv("CGB_FORCE_PIVOT", "1")
+    cg.set_debug(force_pivot=True)
     piv = logp(c["x"][:nb], c["params"], c["state_idx"][:nb])
-    monkeypatch.delenv("CGB_FORCE_PIVOT")
+    cg.set_debug(force_pivot=False)
     assert np.abs(piv - c["ref_logp"]).max() < RTOL * np.abs(c["ref_logp"]).max()
     assert np.abs(piv - fast).max() < 1e-4
     # wild weights: strongly non-identity Jacobian
@@ -277,8 +277,8 @@ def test_potential_stats_single_process(cg):
 @pytest.mark.parametrize("tag", ["n13_rs10", "n29_rs1"])
 def test_cta_kernel_still_matches_golden(cg, cases, tag, monkeypatch):
     """n = 13 / 29 are dispatched to the warp-per-walker kernel; the CTA-per-walker kernel (used for every other n)
-    must keep reproducing the reference's own run on the same shapes (CGB_SWEEP_KERNEL=cta forces it)."""
-    monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
+    must keep reproducing the reference's own run on the same shapes (cg.set_sweep_kernel("cta") forces it)."""
+    cg.set_sweep_kernel("cta")
     c = cases(tag)
     nb = c["mc_x0"].shape[0]
     logp = cg.make_logp(c["ktable"], c["L"])
@@ -302,9 +302,9 @@ def test_ready_queue_any_batch_size(cg, cases, B, monkeypatch):
     x0 = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2))
     si = np.tile(c["state_idx"], (reps, 1))[:B]
     logp = cg.make_logp(c["ktable"], c["L"])
-    monkeypatch.setenv("CGB_SWEEP_KERNEL", "warp")
+    cg.set_sweep_kernel("warp")
     xw, accw, trw = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, return_trace=True)
-    monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
+    cg.set_sweep_kernel("cta")
     xc, accc, trc = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, return_trace=True)
     assert (np.abs(trw["logp_prop"][0] - trc["logp_prop"][0]) < RTOL * np.abs(trc["logp_prop"][0])).all()
     same = (trw["accept"] == trc["accept"]).all(axis=0)
@@ -330,7 +330,7 @@ def test_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeypatch):
     noise, unif = rng.standard_normal((S, B, c["n"], 2)), rng.uniform(size=(S, B))
     out = {}
     for k in ("warp", "spec4", "spec8"):
-        monkeypatch.setenv("CGB_SWEEP_KERNEL", k)
+        cg.set_sweep_kernel(k)
         out[k] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 1234, S, 0.1, return_trace=True)
         out[k + "_explicit"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), cg.ExplicitNoise(noise, unif), S, 0.1,
                                        return_trace=True)
@@ -349,7 +349,7 @@ def test_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeypatch):
 def test_cluster_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeypatch):
     """CTA-per-walker kernel, speculative mode: a thread-block cluster of 4 / 8 CTAs per walker evaluates the decision
     tree of the next steps at once (log p exchanged through distributed shared memory, one cluster barrier per round).
-    Must give exactly the chain of the sequential CTA kernel (CGB_SWEEP_KERNEL=cta): identical accept masks and final
+    Must give exactly the chain of the sequential CTA kernel (set_sweep_kernel("cta")): identical accept masks and final
     walkers; log p to float64 rounding (the two template instantiations contract a few float64 FMAs differently: 1e-13).
     When the clusters of the whole batch are not resident at once the library falls back to the sequential kernel
     (B = 400 at n = 57), same answer."""
@@ -362,7 +362,7 @@ def test_cluster_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeyp
     noise, unif = rng.standard_normal((S, B, c["n"], 2)), rng.uniform(size=(S, B))
     out = {}
     for k in ("cta", "cta4", "cta8"):
-        monkeypatch.setenv("CGB_SWEEP_KERNEL", k)
+        cg.set_sweep_kernel(k)
         out[k] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 4321, S, 0.1, return_trace=True)
         out[k + "_explicit"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), cg.ExplicitNoise(noise, unif), S, 0.1,
                                        return_trace=True)
@@ -390,12 +390,12 @@ def test_other_warp_kernel_instances(cg, oracle, n, monkeypatch):
     x0 = rng.uniform(0, L, (B, n, 2))
     si = np.stack([np.sort(rng.choice(kt.shape[0], n, replace=False)) for _ in range(B)]).astype(np.int32)
     logp = cg.make_logp(kt, L)
-    monkeypatch.setenv("CGB_SWEEP_KERNEL", "warp")
+    cg.set_sweep_kernel("warp")
     lp = logp(x0, p, si)
     ref = oracle["logpsi"].logp_batch(x0[:6], p, si[:6], kt, L)
     assert np.abs(lp[:6] - ref).max() < RTOL * max(1.0, np.abs(ref).max())
     xw, accw, trw = cg.mcmc(logp.bind(p, si), x0.copy(), 7, S, 0.1, return_trace=True)
-    monkeypatch.setenv("CGB_SWEEP_KERNEL", "cta")
+    cg.set_sweep_kernel("cta")
     lpc = logp(x0, p, si)
     assert np.abs(lp - lpc).max() < RTOL * max(1.0, np.abs(lpc).max())
     xc, accc, trc = cg.mcmc(logp.bind(p, si), x0.copy(), 7, S, 0.1, return_trace=True)

@@ -11,24 +11,10 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, load_van  # noqa: F401
 from oracle import van as ovan
 
 VAN_CASES = ["n13_pretrained", "n29_rs1", "n57_rs0.25"]
-
-
-def load_van(tag):
-    z = np.load(os.path.join(GOLDEN, "van_%s.npz" % tag))
-    d = {k: z[k] for k in z.files if not k.startswith("param:")}
-    p = {}
-    for k in z.files:
-        if k.startswith("param:"):
-            _, mod, leaf = k.split(":")
-            p.setdefault(mod, {})[leaf] = z[k]
-    d["params"] = p
-    for k in ("n", "M", "Emax"):
-        d[k] = int(d[k])
-    return d
 
 
 def rand_params(rng, M, scale=0.4):

@@ -3,10 +3,10 @@
 FFMA / MUFU / DFMA micro-benchmarks.  Writes gpurun_out/diag.txt."""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case, CASES_2D
+from coulombgas_b200.fixtures import load_case, CASES_2D
 from oracle import logpsi as ol
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

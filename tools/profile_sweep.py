@@ -3,14 +3,15 @@
 usage: python tools/profile_sweep.py [case] [B] [mc_steps]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case
+from coulombgas_b200.fixtures import load_case
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "n29_rs1"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+if len(sys.argv) > 4: cg.set_sweep_kernel(sys.argv[4])
 c = load_case(tag)
 reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
 x = torch.as_tensor(np.tile(c["x"], (reps, 1, 1))[:B], device="cuda")

@@ -2,10 +2,10 @@
 """Tiny driver for ncu: VAN sampler at a shipped shape.  usage: python tools/profile_van.py [tag] [B]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import torch
 import coulombgas_b200 as cg
-from test_van import load_van
+from coulombgas_b200.fixtures import load_van
 tag = sys.argv[1] if len(sys.argv) > 1 else "n29_rs1"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 c = load_van(tag)

@@ -17,6 +17,8 @@ for l in txt[start + 1:]:
     if m: rows.append((cur, m.group(1).strip()))
     elif l.strip().startswith(".L_"): rows.append((cur, l.strip()))
 main = os.path.basename([a for a in sys.argv if a.endswith(".o")][0]).replace(".o", ".cu")
+for a in sys.argv:
+    if a.startswith("--src="): main = a[6:]
 idx = [i for i, (c, t) in enumerate(rows) if c[0] == main and lo <= c[1] <= hi]
 a, b = min(idx), max(idx)
 ops = collections.Counter()

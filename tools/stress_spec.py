@@ -4,10 +4,10 @@ seed), throughput-mode Philox streams; accept masks and final walkers must be id
 usage: python tools/stress_spec.py [trials]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case
+from coulombgas_b200.fixtures import load_case
 
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(2026)
@@ -26,17 +26,17 @@ for it in range(trials):
     logp = cg.make_logp(c["ktable"], c["L"])
     groups = [("cta", ("cta4", "cta8"))] + ([("warp", ("spec4", "spec8"))] if c["n"] <= 32 else [])
     for ref, others in groups:
-        os.environ["CGB_SWEEP_KERNEL"] = ref
+        cg.set_sweep_kernel(ref)
         xr, ar, tr = cg.mcmc(logp.bind(c["params"], si), x0.copy(), seed, S, sd, return_trace=True)
         for k in others:
-            os.environ["CGB_SWEEP_KERNEL"] = k
+            cg.set_sweep_kernel(k)
             xk, ak, tk = cg.mcmc(logp.bind(c["params"], si), x0.copy(), seed, S, sd, return_trace=True)
             ok = np.array_equal(tr["accept"], tk["accept"]) and np.array_equal(xr, xk) and np.array_equal(tr["naccept"], tk["naccept"]) \
                 and np.abs(tr["logp_prop"] - tk["logp_prop"]).max() <= 1e-11 * np.abs(tr["logp_prop"]).max()
             if not ok:
                 bad += 1
                 print("MISMATCH", tag, B, S, sd, seed, ref, k, flush=True)
-    os.environ.pop("CGB_SWEEP_KERNEL", None)
+    cg.set_sweep_kernel(None)
     xa, aa, ta = cg.mcmc(logp.bind(c["params"], si), x0.copy(), seed, S, sd, return_trace=True)      # the library's own choice
     if not (np.array_equal(ta["accept"], tr["accept"]) or c["n"] <= 32):
         bad += 1

@@ -2,10 +2,10 @@
 """Time the sweep and Ewald kernels on every BASELINE.json config shape (named per-GPU batch and a saturating batch)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case
+from coulombgas_b200.fixtures import load_case
 
 def timeit(fn, reps=3):
     fn(); torch.cuda.synchronize()

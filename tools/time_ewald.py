@@ -4,10 +4,10 @@ is idle), (b) R back-to-back calls per event pair (steady-state API throughput),
 CUDA graph (device time of the kernel alone).  usage: python tools/time_ewald.py [case] [B ...]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case
+from coulombgas_b200.fixtures import load_case
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "n29_rs1"
 Bs = [int(a) for a in sys.argv[2:]] or [2048, 8192]

@@ -4,10 +4,10 @@
 the next 2-3 steps' proposals at once) beat the ready-queue warp-per-walker kernel (throughput).  50-proposal sweeps."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case
+from coulombgas_b200.fixtures import load_case
 
 def timeit(fn, reps=3):
     fn(); torch.cuda.synchronize()
@@ -32,9 +32,9 @@ for tag, Bs in (("n13_rs10", (32, 64, 100, 148, 256, 444, 512, 768, 888, 1024)),
         names = [k for k in KERNELS if c["n"] <= 32 or not (k.startswith("spec") or k == "warp")]
         for k in names:
             if k == "auto":
-                os.environ.pop("CGB_SWEEP_KERNEL", None)
+                cg.set_sweep_kernel(None)
             else:
-                os.environ["CGB_SWEEP_KERNEL"] = k
+                cg.set_sweep_kernel(k)
             out.append(timeit(lambda: cg.mcmc(bound, x.clone(), 3, 50, 0.1)))
         print("%-10s B=%5d  " % (tag, B) + "  ".join("%s %6.3f" % (k, v) for k, v in zip(names, out)) +
               "  ms -> %s" % names[int(np.argmin(out[:-1]))], flush=True)

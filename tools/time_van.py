@@ -2,10 +2,10 @@
 """Timing of the VAN sampler kernel (draw of the n occupied orbitals + log_prob) at the shipped shapes."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from test_van import load_van
+from coulombgas_b200.fixtures import load_van
 
 def timeit(fn, reps=5):
     fn(); torch.cuda.synchronize()

@@ -3,10 +3,10 @@
 usage: python tools/wtune.py case B [B ...]   (env knobs are read by the library at launch time)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import coulombgas_b200 as cg
-from conftest import load_case
+from coulombgas_b200.fixtures import load_case
 
 tag = sys.argv[1]
 c = load_case(tag)
