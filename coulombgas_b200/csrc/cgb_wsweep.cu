@@ -166,6 +166,19 @@ __device__ __forceinline__ double2 lds_pinned_d2(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
     return v;
 }
+// predicated shared-memory store (no divergent branch around a single-lane publish)
+__device__ __forceinline__ void sts_pred_f4(unsigned addr, const float4 v, const bool pred) {
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.shared.v4.f32 [%0], {%1, %2, %3, %4}; }"
+                 :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void sts_pred_f2x2(unsigned addr, const float2 a, const float2 b, const bool pred) {
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.shared.v4.f32 [%0], {%1, %2, %3, %4}; }"
+                 :: "r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void sts_pred_f2(unsigned addr, const float2 a, const bool pred) {
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p st.shared.v2.f32 [%0], {%1, %2}; }"
+                 :: "r"(addr), "f"(a.x), "f"(a.y), "r"((int)pred) : "memory");
+}
 // packed FP32 FMA of sm_100 (FFMA2: two IEEE fmas per lane and instruction; the scalar operand is broadcast by the
 // instruction itself, `R.F32`): same results as two fmaf, half the issue slots
 __device__ __forceinline__ float2 ffma2s(const float a, const float2 b, const float2 c) {
@@ -539,6 +552,7 @@ wsweep_kernel(const SweepParams p) {
 
     const bool rv = lane < N;
     const int kself = rv ? lane : N - 1;
+    const unsigned lanebits = 0xffffffe0u | (unsigned)lane;   // lane-dependent (not warp-uniform) mask for the prefetch keep-alive uses
     const float invn = 1.f / (float)N;
     const double invL = 1.0 / p.L;
     const double nlogL = (double)N * log(p.L);               // D carries L^{-dim/2} per entry (slater.py:17)
@@ -1210,6 +1224,7 @@ wsweep_kernel(const SweepParams p) {
 #pragma unroll
             for (int j = 0; j < N; ++j) Jr[j] = sJ[kself * PB + j];
             bool bad = false;
+            unsigned lu_chk = 0u;
             float4* const line0 = reinterpret_cast<float4*>(sm + L_::o_H);      // [2][LP]: blocks 1..N-1 (+ prefetch padding)
             auto neg_inv = [&](const float4 pk) -> float4 {
                 const float det = pk.x * pk.w - pk.y * pk.z;
@@ -1235,18 +1250,18 @@ wsweep_kernel(const SweepParams p) {
                 const float l00 = fmaf(a.x, m.x, a.y * m.z), l01 = fmaf(a.x, m.y, a.y * m.w);
                 const float l10 = fmaf(a.z, m.x, a.w * m.z), l11 = fmaf(a.z, m.y, a.w * m.w);
                 bad |= act && fmaxf(fmaxf(fabsf(l00), fabsf(l01)), fmaxf(fabsf(l10), fabsf(l11))) > 2.f;
-                float4 pq[4] = {cur[1], cur[2], cur[3], cur[4]};
+                const unsigned nxt32 = (unsigned)__cvta_generic_to_shared(nxt);
+                const bool pub = lane == k + 1;                               // the next pivot row publishes its row as it is updated
+                float4 pq[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) pq[t] = lds_pinned_f4(cur32 + 16u * (unsigned)(1 + t));
 #pragma unroll
                 for (int j0 = 1; j0 < N; j0 += 4) {
                     if (j0 > lim) break;                                      // warp-uniform; at most three dead blocks of work
                     float4 nq[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t)                               // next chunk ahead of its use (line is padded)
-#if CGBW_PIN_LDS
                         nq[t] = lds_pinned_f4(cur32 + 16u * (unsigned)(j0 + 4 + t));
-#else
-                        nq[t] = cur[j0 + 4 + t];
-#endif
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const int j = j0 + t;
@@ -1259,21 +1274,16 @@ wsweep_kernel(const SweepParams p) {
                             v = make_float4(vt.x, vt.y, vb.x, vb.y);
                             Jr[j - 1] = v;
                             if (j == 1) m = neg_inv(shfl4w(v, k + 1));        // next pivot block, inverted by every lane
+                            else sts_pred_f4(nxt32 + 16u * (unsigned)(j - 1), v, pub);
                         }
                     }
+                    lu_chk ^= __float_as_uint(nq[3].w) & lanebits;   // a (per-lane) use inside this block keeps the prefetch where it is written
 #pragma unroll
                     for (int t = 0; t < 4; ++t) pq[t] = nq[t];
                 }
-                if (lane == k + 1) {
-#pragma unroll
-                    for (int j = 1; j < N - 1; ++j) {
-                        if ((j & 3) == 1 && j >= lim) break;
-                        nxt[j] = Jr[j];
-                    }
-                }
                 __syncwarp();
             }
-            bad = __any_sync(FULL, bad && rv) || (p.force_pivot != 0);
+            bad = __any_sync(FULL, bad && rv) || (p.force_pivot != 0) || lu_chk == 0x7fc0dead;    // (lu_chk: never true)
             if (bad) {                              // rare: redo with the partially pivoted LU on the staged copy
                 lacc = pivoted_lu_smem<N>(reinterpret_cast<float*>(sJ), lane);     // all 32 lanes own scalar rows here
                 lacc_per_lane = true;
@@ -1340,6 +1350,7 @@ wsweep_kernel(const SweepParams p) {
             bool done = !rv, singular = false;
             float mypn = 1.f, myerr = 0.f;
             unsigned chk = 0u;
+            const float fone = p.B > 0 ? 1.f : 2.f;             // 1, opaque to the compiler
             float pn, rinv;
             float2 own;
             auto offer = [&](const float2 e) -> unsigned {
@@ -1363,13 +1374,16 @@ wsweep_kernel(const SweepParams p) {
                 const float2* cur = fline0 + (k & 1) * LP;
                 float2* nxt = fline0 + ((k + 1) & 1) * LP;
                 const unsigned cur32 = (unsigned)__cvta_generic_to_shared(cur);
+                const unsigned nxt32 = (unsigned)__cvta_generic_to_shared(nxt);
                 const int lim = N - 1 - k;
                 singular |= (wk >> 5) == 0u;
                 done |= win;
                 if (lim == 0) break;
                 const float2 c = Dr[0];
                 const float2 L1 = make_float2(-(c.x * iv.x - c.y * iv.y), -(c.x * iv.y + c.y * iv.x));   // l = -c / pivot
-                const float2 L2 = make_float2(-L1.y, L1.x);
+                // i l as a register pair of its own (the products by a run-time 1 keep ptxas from re-deriving it from L1 by operand
+                // modifiers, which costs a pair copy per packed FMA)
+                const float2 L2 = make_float2(-L1.y * fone, L1.x * fone);
                 float4 pq[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) pq[t] = lds_pinned_f4(cur32 + 16u + 16u * (unsigned)t);       // entries 1..8
@@ -1394,14 +1408,16 @@ wsweep_kernel(const SweepParams p) {
                             }
                         }
                     }
-                    if (win) {                                    // the next pivot row publishes this chunk of its row
+                    // the next pivot row publishes this chunk of its row (predicated, no divergence): new register r (= j - 1) is
+                    // entry r of the next line, slot r + 1; slots of odd r are 16-byte aligned: three pair stores + two singles
+                    if (j0 > 1 && j0 - 1 < N - 1) sts_pred_f2(nxt32 + 8u * (unsigned)j0, Dr[j0 - 1], win);
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int j = j0 + t;
-                            if (j >= 2 && j < N) nxt[j] = Dr[j - 1];          // entry j - 1 of the next line
-                        }
+                    for (int r = j0; r < j0 + 6; r += 2) {
+                        if (r + 1 < N - 1) sts_pred_f2x2(nxt32 + 8u * (unsigned)(r + 1), Dr[r], Dr[r + 1], win);
+                        else if (r < N - 1) sts_pred_f2(nxt32 + 8u * (unsigned)(r + 1), Dr[r], win);
                     }
-                    chk ^= __float_as_uint(nq[3].w);              // a use inside this block keeps the prefetch where it is written
+                    if (j0 + 6 < N - 1) sts_pred_f2(nxt32 + 8u * (unsigned)(j0 + 7), Dr[j0 + 6], win);
+                    chk ^= __float_as_uint(nq[3].w) & lanebits;       // a (per-lane) use inside this block keeps the prefetch where it is written
 #pragma unroll
                     for (int t = 0; t < 4; ++t) pq[t] = nq[t];
                 }
