@@ -44,6 +44,8 @@ struct WConst {
     float w1b[16][16];    // W1[16:32]         acts on mean_k h_k
     float w1c[16][16];    // W1[32:48]         acts on mean_j t_ij
     float wf[16][2];      // Wf
+    double expc[11];      // Taylor coefficients 1/10! .. 1/0! of the float64 exp (single-particle stream): constant-bank operands
+    double logc[11];      // 1/21, 1/19, .., 1/3, 1 of the float64 log1p series
     float sabM[16];       // pass 1: magic constant 2^e >= max |a_c| of channel c (fixed-point accumulation of sum_k |a_k|)
     double sabS[16];      // ... and the weight 2^(e-23) of one unit of that fixed-point sum
     double dw0c[5][16];
@@ -105,6 +107,10 @@ __global__ void wsweep_prologue_kernel(const double* __restrict__ p, WConst* __r
         (&w->w1c[0][0])[t] = (float)p[S_W1 + 512 + t];
         (&w->dw1a[0][0])[t] = p[S_W1 + t];
         (&w->dw1c[0][0])[t] = p[S_W1 + 512 + t];
+    }
+    if (threadIdx.x == 0) {
+        double f = 1.0;
+        for (int t = 0; t <= 10; ++t) { w->expc[10 - t] = 1.0 / f; f *= (double)(t + 1); w->logc[10 - t] = 1.0 / (double)(2 * t + 1); }
     }
     for (int t = threadIdx.x; t < 32; t += blockDim.x) {
         (&w->wf[0][0])[t] = (float)p[S_WF + t];
@@ -238,33 +244,17 @@ __device__ __forceinline__ void softplus_sigmoid_f64w(double pre, double& sp, fl
     const double y = fmax(-fabs(pre) * 1.4426950408889634074, -1000.0);
     const double kf = rint(y);
     const double f = (y - kf) * 0.69314718055994530942;
-    double pz = 2.7557319223985891e-07;
-    pz = fma(pz, f, 2.7557319223985893e-06);
-    pz = fma(pz, f, 2.4801587301587302e-05);
-    pz = fma(pz, f, 1.9841269841269841e-04);
-    pz = fma(pz, f, 1.3888888888888889e-03);
-    pz = fma(pz, f, 8.3333333333333332e-03);
-    pz = fma(pz, f, 4.1666666666666664e-02);
-    pz = fma(pz, f, 1.6666666666666666e-01);
-    pz = fma(pz, f, 0.5);
-    pz = fma(pz, f, 1.0);
-    pz = fma(pz, f, 1.0);
+    double pz = cW.expc[0];
+#pragma unroll
+    for (int q = 1; q <= 10; ++q) pz = fma(pz, f, cW.expc[q]);
     const double t = pz * __hiloint2double(((int)kf + 1023) << 20, 0);
     const double d = 2.0 + t;
     const double r0 = (double)rcp_approx((float)d);
     const double r = fma(r0, fma(-d, r0, 1.0), r0);
     const double u = t * r, w = u * u;
-    double a = 4.7619047619047616e-02;
-    a = fma(a, w, 5.2631578947368418e-02);
-    a = fma(a, w, 5.8823529411764705e-02);
-    a = fma(a, w, 6.6666666666666666e-02);
-    a = fma(a, w, 7.6923076923076927e-02);
-    a = fma(a, w, 9.0909090909090912e-02);
-    a = fma(a, w, 1.1111111111111111e-01);
-    a = fma(a, w, 1.4285714285714285e-01);
-    a = fma(a, w, 0.2);
-    a = fma(a, w, 3.3333333333333331e-01);
-    a = fma(a, w, 1.0);
+    double a = cW.logc[0];
+#pragma unroll
+    for (int q = 1; q <= 10; ++q) a = fma(a, w, cW.logc[q]);
     sp = fmax(pre, 0.0) + 2.0 * u * a;
     const float ef = (float)t, rr = rcp_approx(1.f + ef);
     sg = pre >= 0.0 ? rr : ef * rr;
@@ -936,9 +926,10 @@ wsweep_kernel(const SweepParams p) {
             for (int k = 0; k < N; ++k) {
                 const float4 pj = pn;
                 pn = sPos[k + 1 < N ? k + 1 : k];
-                if (k != kself) {
+                {   // branch-free: the diagonal partner (sh = 0: e4 = 0 * finite) contributes exact zeros
                     const WHalf hd = whalf_diff(pos, npc, pj);
-                    const float ai4d = (-0.5f * alpha) * rsqrt_approx(fmaf(hd.sh.x, hd.sh.x, hd.sh.y * hd.sh.y));     // -alpha / (4 d) * 2
+                    const float d2s = k != kself ? fmaf(hd.sh.x, hd.sh.x, hd.sh.y * hd.sh.y) : 1.f;
+                    const float ai4d = (-0.5f * alpha) * rsqrt_approx(d2s);                                         // -alpha / (4 d) * 2
                     const float2 e4 = __fmul2_rn(__fmul2_rn(hd.sh, hd.ch), make_float2(ai4d, ai4d));                  // -alpha sin(th)/(4 d)
                     const float e4x = e4.x, e4y = e4.y;
 #pragma unroll
@@ -1079,13 +1070,15 @@ wsweep_kernel(const SweepParams p) {
             for (int k = 0; k < N; ++k) {
                 const float4 pj = pn;
                 pn = sPos[k + 1 < N ? k + 1 : k];
-                if (k != kself) {
+                {   // no branch around the diagonal partner: its lane computes a harmless dummy block that is neither stored nor summed
+                    const bool offd = k != kself;
                     const WPairFeat f = wpair_features(pos, npc, pj);
-                    const float i4d = 0.25f * rsqrt_approx(f.d2);
+                    const float d2s = offd ? f.d2 : 1.f;
+                    const float i4d = 0.25f * rsqrt_approx(d2s);
                     // E_ik = (1/n) d t0_ik / d x_k   (5x2, 6 non-zeros)
                     const float2 e01 = __fmul2_rn(f.s, make_float2(alpha, alpha)), e23 = __fmul2_rn(f.c, make_float2(-alpha, -alpha));
                     const float2 e4 = __fmul2_rn(e01, make_float2(-i4d, -i4d));
-                    const float d = f.d2 * (4.f * i4d);
+                    const float d = d2s * (4.f * i4d);
                     float2 U[5];
 #pragma unroll
                     for (int g = 0; g < 5; ++g) U[g] = Q2[g];
@@ -1113,8 +1106,9 @@ wsweep_kernel(const SweepParams p) {
                         jx = ffma2s(hv.x, T2[2 * c2], ffma2s(hv.z, T2[2 * c2 + 1], jx));
                         jy = ffma2s(hv.y, T2[2 * c2], ffma2s(hv.w, T2[2 * c2 + 1], jy));
                     }
-                    if (rv) sJ[lane * PB + k] = make_float4(jx.x, jy.x, jx.y, jy.y);
-                    rsx = __fadd2_rn(rsx, jx); rsy = __fadd2_rn(rsy, jy);
+                    if (rv && offd) sJ[lane * PB + k] = make_float4(jx.x, jy.x, jx.y, jy.y);
+                    const float2 z2 = make_float2(0.f, 0.f);
+                    rsx = __fadd2_rn(rsx, offd ? jx : z2); rsy = __fadd2_rn(rsy, offd ? jy : z2);
                 }
             }
             // translation equivariance: sum_k J_ik = I  (reference tests/test_flow.py:29-32)
