@@ -3,18 +3,28 @@
 
 One "step" = one sampling step of the reference's training loop for this rank's shard of walkers
 (main.py:334-338 -> src/VMC.py:8-25 -> src/MCMC.py): a Metropolis sweep of mc_steps=50 all-electron proposals
-(51 evaluations of log p per walker) followed by one Ewald energy evaluation of the final walkers
-(src/VMC.py:40).  Workload = BASELINE.json configs[2]: n=29, dim 2, rs=1, Emax=25 (M=81), Gmax=15 (|G|=708),
-kappa=10, batch 2048 walkers per GPU (weak scaling: every rank holds a full 2048-walker batch).
+(51 evaluations of log p per walker), the wrap into [0,L), one Ewald energy evaluation of the final walkers
+(src/VMC.py:40) and ONE all-reduce of the 5-entry statistics vector (accept rate, V mean, V^2 mean: the pmean sites
+of src/MCMC.py:39 and src/VMC.py:46-53).  Per step: 3 kernel launches of libcgb200.so (prologue, sweep, Ewald) + one
+constant-bank memcpy, captured in a CUDA graph; the per-device PRNG key lives on the device.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1..c5] [--scaling weak|strong] [--batch B]
+                  [--impl ours|reference]
   torchrun ... bench.py --gpus N ...      (one rank per GPU, NCCL)
 
-Prints ONE JSON line (rank 0).  `value` = walker-steps/s with inputs resident in HBM (device timed, CUDA events
-on the launching stream, max over ranks); `e2e` = the same through the public host-buffer API with H2D/D2H
-copies inside the timed region; `roofline` = FP32 work rate of the sweep kernel vs the FFMA peak measured by
-a saturating micro-kernel in this same process; `cpu_baseline` = the float64 restated reference algorithm
-(oracle/) timed on this box's host cores on a bounded sample.  --impl reference times that CPU path alone.
+Workloads (BASELINE.json configs[0..4] = c1..c5); default c3 = the configuration the metric is quoted on:
+  c1 n=13 rs=10 Emax=25 batch 256   c2 n=13 rs=10 Emax=25 batch 4096   c3 n=29 rs=1 Emax=25 batch 2048
+  c4 n=49 rs=0.5 Emax=36 batch 512  c5 n=57 rs=0.25 Emax=49 batch 512      (dim 2, Gmax=15, kappa=10, mc_steps 50)
+--scaling weak (default): every rank holds the config's batch (value = N x batch x 50 / time);
+--scaling strong: the config's batch is the GLOBAL batch, sharded over the ranks exactly as main.py:231-238 does.
+The line always carries both: `value` for the chosen mode and a "strong" / "weak" companion object for the other.
+
+Prints ONE JSON line (rank 0).  `value` = walker-steps/s with inputs resident in HBM (device timed, CUDA events on the
+launching stream, max over ranks); `e2e` = the same through the public host-buffer API with H2D/D2H copies inside the
+timed region; `roofline` = FP32 work rate of the sweep kernel vs the FFMA peak measured by a saturating micro-kernel in
+this same process; `parity` = the benchmarked kernel at the benchmarked shape against the float64 oracle on identical
+walkers, noise and uniforms (mismatch fraction of the accept masks, max relative error of log p); `cpu_baseline` = the
+oracle's timing on this box's host cores on that same bounded sample.  --impl reference times that CPU path alone.
 """
 import argparse
 import json
@@ -26,21 +36,28 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-CFG = dict(tag="n29_rs1", n=29, dim=2, rs=1.0, Emax=25, Gmax=15, kappa=10, mc_steps=50, mc_stddev=0.1, batch=2048)
+CONFIGS = {
+    "c1": dict(tag="n13_rs10", n=13, rs=10.0, Emax=25, batch=256, devices=1, name="configs[0]"),
+    "c2": dict(tag="n13_rs10", n=13, rs=10.0, Emax=25, batch=4096, devices=8, name="configs[1]"),
+    "c3": dict(tag="n29_rs1", n=29, rs=1.0, Emax=25, batch=2048, devices=8, name="configs[2]"),
+    "c4": dict(tag="n49_rs0.5", n=49, rs=0.5, Emax=36, batch=512, devices=8, name="configs[3]"),
+    "c5": dict(tag="n57_rs0.25", n=57, rs=0.25, Emax=49, batch=512, devices=8, name="configs[4]"),
+}
+COMMON = dict(dim=2, Gmax=15, kappa=10, mc_steps=50, mc_stddev=0.1)
 METRIC = "metropolis_walker_steps_per_sec"
 UNIT = "walker-steps/s"
+CPU_SAMPLE_WALKERS = {13: 128, 29: 64, 49: 24, 57: 16}      # oracle sample: these walkers x the full 50-step chain (~10-30 s)
 
 
-def load_inputs(B, rank=0):
-    """Synthetic inputs of the named shape: the shipped checkpoint walkers (device-0 shard, 256
-    walkers) tiled to B with seeded N(0,0.1^2) jitter; trained flow parameters; state_idx even=ground state,
-    odd=sorted random subset."""
-    from conftest import load_case
-    c = load_case(CFG["tag"])
+def load_inputs(cfg, B, rank=0):
+    """Synthetic inputs of the named shape: the shipped checkpoint walkers tiled to B with seeded
+    N(0,0.1^2) jitter; trained flow parameters (init-scale for n=13: no shipped flow checkpoint); state_idx even=ground
+    state, odd=sorted random subset."""
+    from coulombgas_b200.fixtures import load_case
+    c = load_case(cfg["tag"])
     rng = np.random.default_rng(42 + rank)
     reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
     x = np.tile(c["x"], (reps, 1, 1))[:B] + 0.1 * rng.standard_normal((B, c["n"], 2))
@@ -53,12 +70,13 @@ def load_inputs(B, rank=0):
     return c, x, si
 
 
-def make_config(B, world):
-    return {"workload": "configs[2]: n=29 dim=2 rs=1.0 Theta=0.15 Emax=25 (M=81) Gmax=15 (|G|=708) kappa=10, "
-                        "batch %d walkers/GPU, mc_steps=50 (51 log p evals/walker) + 1 Ewald eval/walker per step" % B,
-            "inputs": "shipped checkpoint walkers tiled + N(0,0.1) jitter, trained flow params, in-kernel Philox",
+def make_config(ckey, cfg, B, world, scaling):
+    return {"workload": "%s (%s): n=%d dim=2 rs=%g Theta=0.15 Emax=%d Gmax=15 (|G|=708) kappa=10, batch %d walkers/GPU "
+                        "(%s scaling: global batch %d), mc_steps=50 (51 log p evals/walker) + 1 Ewald eval/walker + 1 all-reduce "
+                        "per step" % (cfg["name"], ckey, cfg["n"], cfg["rs"], cfg["Emax"], B, scaling, B * world),
+            "inputs": "shipped checkpoint walkers tiled + N(0,0.1) jitter, trained flow params, in-kernel Philox (device key)",
             "l2": "256 MiB write between timed iterations (L2 flush); working set itself is < L2",
-            "parallelism": "dp%d (walkers sharded, 2 scalar all-reduces/step)" % world}
+            "parallelism": "dp%d (walkers sharded, 1 all-reduce of 5 doubles per step)" % world}
 
 
 class ClockSampler(threading.Thread):
@@ -100,54 +118,84 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(c, x, si, G, walkers, mc_steps, threads):
-    """The restated reference algorithm (oracle/: vmap'd flow + jacfwd + LAPACK slogdet, Metropolis step,
-    pairwise-cos Ewald) on `threads` host cores.  Returns (walker-steps/s, ewald evals/s, seconds)."""
+def oracle_sample(c, x, si, noise, unif, walkers, threads):
+    """The restated reference algorithm (oracle/: vmap'd flow + jacfwd + LAPACK slogdet, Metropolis chain of the FULL
+    mc_steps, pairwise-cos Ewald) on `threads` host cores for the first `walkers` walkers of the batch.
+    Returns (trace dict, x_final, V, seconds for the sweep, seconds for the Ewald)."""
     import torch
-    from oracle import logpsi as ol, mcmc as om, potential as op
+    from oracle import logpsi as ol, mcmc as om, potential as op, tables
     torch.set_num_threads(threads)
-    rng = np.random.default_rng(7)
+    S = noise.shape[0]
     xs, sis = x[:walkers], si[:walkers]
-    noise, unif = rng.standard_normal((mc_steps, walkers, c["n"], 2)), rng.random((mc_steps, walkers))
     lp = lambda y: ol.logp_batch(y, c["params"], sis, c["ktable"], c["L"], chunk=32)
     ol.logp_batch(xs[:2], c["params"], sis[:2], c["ktable"], c["L"])     # warm-up (torch.func first-call overhead)
     t0 = time.perf_counter()
-    xo, acc = om.mcmc(lp, xs, noise, unif, mc_steps, CFG["mc_stddev"])
+    xo, acc, tr = om.mcmc(lp, xs, noise[:, :walkers], unif[:, :walkers], S, COMMON["mc_stddev"], trace=True)
     t1 = time.perf_counter()
-    op.potential_energy(om.wrap(xo, c["L"]), c["kappa"], G, c["L"], c["rs"])
+    G = tables.kpoints(2, COMMON["Gmax"])
+    V = op.potential_energy(om.wrap(xo, c["L"]), c["kappa"], G, c["L"], c["rs"])
     t2 = time.perf_counter()
-    # walker-steps/s for a full sampling step: sweep of mc_steps proposals (+1 initial eval) + Ewald
-    per_walker = (t1 - t0) / walkers * (CFG["mc_steps"] + 1) / (mc_steps + 1) + (t2 - t1) / walkers
-    return CFG["mc_steps"] / per_walker, walkers / (t2 - t1), t2 - t0
+    return tr, xo, V, t1 - t0, t2 - t1
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  JAX/jaxlib/haiku are not installable
-    in this image (no wheels, no network), so this is the float64 restatement of the reference
-    algorithm as written (oracle/), all host threads, on a bounded sample of the same workload."""
+def parity_report(trg, tro, unif, walkers, rtol=1e-5):
+    """Free-running comparison of the GPU chain with the oracle chain up to the first divergence of each walker
+    (tests/test_gpu_parity.py::test_mcmc_vs_oracle): mismatching decisions are legitimate only at near-ties."""
+    S = tro["accept"].shape[0]
+    acc_g, acc_r = trg["accept"][:, :walkers].astype(bool), tro["accept"]
+    diverged = np.zeros(walkers, bool)
+    mism = near = compared = 0
+    max_rel = 0.0
+    for s in range(S):
+        live = ~diverged
+        ref = tro["logp_prop"][s][live]
+        if live.any():
+            max_rel = max(max_rel, float(np.max(np.abs(trg["logp_prop"][s + 1][:walkers][live] - ref) / np.abs(ref))))
+        bad = live & (acc_g[s] != acc_r[s])
+        compared += int(live.sum())
+        if bad.any():
+            prev = tro["logp_init"] if s == 0 else tro["logp"][s - 1]
+            margin = np.abs((tro["logp_prop"][s] - prev) - np.log(unif[s][:walkers]))[bad]
+            near += int((margin < 2 * rtol * np.abs(tro["logp_prop"][s][bad])).sum())
+        mism += int(bad.sum())
+        diverged |= bad
+    return {"walkers": walkers, "mc_steps": S, "decisions_compared": compared, "accept_mismatch_frac": mism / max(compared, 1),
+            "mismatches": mism, "mismatches_at_near_ties": near, "max_rel_logp_err": max_rel, "tolerance": rtol,
+            "walkers_identical_to_the_end": int((~diverged).sum())}
+
+
+def run_reference(args, ckey, cfg):
+    """--impl reference: the reference's CPU implementation of the path.  JAX/jaxlib/haiku are not installable in this
+    image (no wheels, no network), so this is the float64 restatement of the reference algorithm as
+    written (oracle/), all host threads, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
-    c, x, si = load_inputs(256)
-    from oracle import tables
-    G = tables.kpoints(2, CFG["Gmax"])
-    walkers, sub_steps = 128, 3
+    B = args.batch or (cfg["batch"] if args.scaling == "weak" else cfg["batch"] // world)
+    c, x, si = load_inputs(cfg, 256)
+    walkers, sub_steps = CPU_SAMPLE_WALKERS[cfg["n"]], 3
+    S = COMMON["mc_steps"]
     vals, secs = [], []
+    rng = np.random.default_rng(7)
     for it in range(args.warmup + args.steps):
-        v, ew, s = cpu_reference_rate(c, x, si, G, walkers, sub_steps, threads)
+        noise, unif = rng.standard_normal((sub_steps, walkers, c["n"], 2)), rng.random((sub_steps, walkers))
+        _, _, _, t_sweep, t_ew = oracle_sample(c, x, si, noise, unif, walkers, threads)
+        per_walker = t_sweep / walkers * (S + 1) / (sub_steps + 1) + t_ew / walkers     # a full step: 51 evals + Ewald
         if it >= args.warmup:
-            vals.append(v); secs.append(s)
+            vals.append(S / per_walker); secs.append(t_sweep + t_ew)
     value = float(np.mean(vals))
+    sample = ("%d walkers x (%d proposals + 1 initial log p) + Ewald per step, scaled to the 50-proposal sweep; "
+              "torch-f64 vmap+jacfwd+LAPACK" % (walkers, sub_steps))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": make_config(args.batch, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d walkers x (%d proposals + 1 initial log p) + Ewald per step, "
-                                       "scaled to the 50-proposal sweep; torch-f64 vmap+jacfwd+LAPACK"
-                                       % (walkers, sub_steps)},
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": world * B * S / value * 1e3,
+            "ms_per_step_note": "extrapolated time of one full step of this arm's batch at the measured rate; the timed "
+                                "sample itself took %.1f ms per repetition" % (float(np.mean(secs)) * 1e3),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": make_config(ckey, cfg, B, world, args.scaling),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -159,11 +207,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=CFG["batch"], help="walkers per GPU")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help="walkers per GPU (overrides the config / scaling rule)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     args = ap.parse_args()
+    ckey, cfg = args.config, CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, ckey, cfg)
 
     import torch
     import torch.distributed as dist
@@ -187,31 +239,59 @@ def main():
         finally:
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    B, S, n = args.batch, CFG["mc_steps"], CFG["n"]
-    c, x_host, si_host = load_inputs(B, rank)
-    G = cg.kpoints(2, CFG["Gmax"])
-    Vconst = n * c["rs"] / c["L"] * cg.madelung(2, CFG["kappa"], G)
+    S, n = COMMON["mc_steps"], cfg["n"]
+    if cfg["batch"] % world != 0:
+        raise SystemExit("Batch size must be divisible by the number of GPU devices (main.py:231-233)")
+    B_weak, B_strong = cfg["batch"], cfg["batch"] // world
+    B = args.batch or (B_weak if args.scaling == "weak" else B_strong)
+    Bmax = max(B, B_weak)
+    c, x_host_all, si_host_all = load_inputs(cfg, Bmax, rank)
+    G = cg.kpoints(2, COMMON["Gmax"])
+    Vconst = n * c["rs"] / c["L"] * cg.madelung(2, COMMON["kappa"], G)
     logp = cg.make_logp(c["ktable"], c["L"])
     params = torch.as_tensor(cg.pack_params(c["params"]), device=dev)
-    si = torch.as_tensor(si_host, device=dev)
-    x0 = torch.as_tensor(x_host, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
-    def step(x, key):
-        key, x, acc = cg.sample_x(key, si, logp, x, params, S, CFG["mc_stddev"], c["L"])     # sweep + wrap + psum
-        V = cg.potential_energy(x, CFG["kappa"], G, c["L"], c["rs"]) + Vconst                 # VMC.py:40
-        vm, v2 = cg.potential_stats(V)                                                        # VMC.py:46-53 (V entries)
-        return key, x, acc, vm, v2
+    def make_step(Bx, seed):
+        x = torch.as_tensor(x_host_all[:Bx], device=dev).clone()
+        si = torch.as_tensor(si_host_all[:Bx], device=dev)
+        st = cg.SamplingStep(logp, si, params, x, cg.device_key(seed + rank), S, COMMON["mc_stddev"], COMMON["kappa"], G,
+                             c["rs"], Vconst)
+        if not args.no_graph:
+            st.capture(warmup=2)
+        return st
 
-    key = 1000 + rank
-    x = x0.clone()
+    def timed(st, steps, warmup):
+        """mean ms per step over `steps` steps (CUDA events around each step, L2 flushed in between), max over ranks"""
+        for _ in range(warmup):
+            st.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            flush.fill_(k & 0xFF)                      # L2 flush between timed iterations (outside the event pair)
+            ev[k][0].record()
+            st.step()
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), wall
+
+    step = make_step(B, 1000)
     for _ in range(args.warmup):
-        key, x, acc, vm, v2 = step(x, key)
+        step.step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
+
     # nvidia-smi needs a moment to start (longer than the whole timed region on a cold box): keep the GPU under the same
     # load with untimed steps until its first sample has arrived, so that the samples that follow fall into the timed region
     def agree(flag):                       # the untimed extra steps contain collectives: every rank must take the same number
@@ -223,38 +303,36 @@ def main():
 
     t_wait = time.perf_counter()
     while agree(not sampler.rows and time.perf_counter() - t_wait < 5.0):
-        key, x, acc, vm, v2 = step(x, key)
+        step.step()
         torch.cuda.synchronize()
     n_before = len(sampler.rows)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)                      # L2 flush between timed iterations (outside the event pair)
-        ev[k][0].record()
-        key, x, acc, vm, v2 = step(x, key)
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    # the timed region is ~0.1 s, nvidia-smi samples every 0.1 s: continue with untimed steps of the same workload until
-    # a few samples under load exist (xk: a copy, so that the reported state is the timed region's)
+    ms, t_wall = timed(step, args.steps, 0)
+    acc_rate, v_mean, v2_mean = step.summary()
     t_wait = time.perf_counter()
-    xk2, key2 = x.clone(), key
     while agree(len(sampler.rows) < n_before + 3 and time.perf_counter() - t_wait < 2.0):
-        key2, xk2, _, _, _ = step(xk2, key2)
+        step.step()
         torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     clocks = sampler.finish()
     clocks["window"] = "timed region, extended by untimed steps of the same workload until nvidia-smi (100 ms period) delivered 3 samples"
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax)
     value = world * B * S / (ms * 1e-3)
 
+    # ---- the other scaling mode beside the headline (same code path, same step)
+    other_mode = "strong" if args.scaling == "weak" else "weak"
+    B_other = B_strong if other_mode == "strong" else B_weak
+    other = None
+    if not args.batch:
+        if B_other == B:
+            other = {"scaling": other_mode, "global_batch": world * B_other, "walkers_per_gpu": B_other, "value": value,
+                     "ms_per_step": ms, "note": "identical to the headline at this N"}
+        else:
+            st_o = make_step(B_other, 3000)
+            ms_o, _ = timed(st_o, args.steps, args.warmup)
+            other = {"scaling": other_mode, "global_batch": world * B_other, "walkers_per_gpu": B_other,
+                     "value": world * B_other * S / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o}
+
     # ---- kernel-only timings for the roofline (sweep kernel alone, Ewald kernel alone), CUDA events
+    x = step.x
+    si = torch.as_tensor(si_host_all[:B], device=dev)
     bound = logp.bind(params, si)
 
     def time_fn(fn, reps):
@@ -267,10 +345,11 @@ def main():
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
     xk = x.clone()
-    ms_sweep = time_fn(lambda: cg.mcmc(bound, xk, 77, S, CFG["mc_stddev"], wrap_L=c["L"]), 5)
+    kkey = cg.device_key(77 + rank)
+    ms_sweep = time_fn(lambda: cg.mcmc(bound, xk, kkey, S, COMMON["mc_stddev"], wrap_L=c["L"], advance_key=True, _want_rate=False), 5)
     # the Ewald kernel runs ~10 us: a single launch per event pair would time the host launch latency, so 20 launches
     # are captured in a CUDA graph and the replay is timed (device time per launch); fallback: 200 back-to-back calls
-    few = lambda: cg.potential_energy(xk, CFG["kappa"], G, c["L"], c["rs"])
+    few = lambda: cg.potential_energy(xk, COMMON["kappa"], G, c["L"], c["rs"])
     ew_reps, ew_mode = 20, "CUDA-graph replay of 20 launches"
     try:
         gs = torch.cuda.Stream()
@@ -290,69 +369,66 @@ def main():
     # ---- the caller right before the sweep (SURVEY §8 f/N2): VAN draw of the occupied orbitals, reported beside the headline
     van_info = None
     try:
-        from test_van import load_van
-        vc = load_van("n29_rs1")
+        from coulombgas_b200.fixtures import load_van
+        vtag = {"n13_rs10": "n13_pretrained"}.get(cfg["tag"], cfg["tag"])
+        vc = load_van(vtag)
         van = cg.VanSampler(vc["ktable"], vc["n"], vc["M"])
         pv = torch.as_tensor(cg.pack_van_params(vc["params"]), device=dev)
-        ms_van = time_fn(lambda: van.sampler(pv, 9, B, return_log_prob=True), 5)
+        ms_van = time_fn(lambda: van.sampler(pv, kkey, B, return_log_prob=True), 5)
         van_info = {"kernel": "van_kernel", "ms": ms_van, "walkers_per_sec": world * B / (ms_van * 1e-3),
-                    "note": "n=29 M=81 draws + log_prob for the same batch; not part of the timed step (north_star keeps the VAN outside the path)"}
+                    "note": "draws + log_prob for the same batch; not part of the timed step (north_star keeps the VAN outside the path)"}
     except Exception as e:                                   # pragma: no cover
         van_info = {"error": repr(e)}
-    # ---- the reference's own per-device shard of this configuration (batch 2048 over 8 GPUs = 256 walkers): latency regime,
-    # the library dispatches it to the speculative mode; reported beside the headline
-    shard_info = None
-    try:
-        Bs = max(1, B // 8)
-        xs_, sis_ = x[:Bs].clone(), si[:Bs].contiguous()
-        bound_s = logp.bind(params, sis_)
-        ms_shard = time_fn(lambda: cg.mcmc(bound_s, xs_, 78, S, CFG["mc_stddev"], wrap_L=c["L"]), 5)
-        shard_info = {"walkers": Bs, "ms": ms_shard, "walker_steps_per_sec": Bs * S / (ms_shard * 1e-3),
-                      "note": "one 50-step sweep of 256 walkers on one GPU (the reference's shard at batch 2048 / 8 devices); "
-                              "speculative Metropolis, 4 warps per walker"}
-    except Exception as e:                                   # pragma: no cover
-        shard_info = {"error": repr(e)}
     blocks = 148 * 8
     ffma = max(2 * 8 * 20000 * blocks * 256 / cg.microbench(0, blocks, 20000) for _ in range(3)) / 1e12
     mufu = max(8 * 20000 * blocks * 256 / cg.microbench(1, blocks, 20000) for _ in range(3)) / 1e12
     flop = cg.flops.flop_sweep(n, S) * B
     achieved = flop / (ms_sweep * 1e-3) / 1e12
-    # DRAM traffic of one sweep launch at this shape, from the committed ncu --set full capture (profiles/)
+    # DRAM traffic of one sweep launch at the headline shape, from the committed ncu --set full capture (profiles/)
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
-    if os.path.exists(tfile):
-        tj = json.load(open(tfile))
-        if tj.get("batch") == B and tj.get("mc_steps") == S:
-            traffic = tj.get("dram_bytes_per_launch")
+    for tname in ("r02_sweep_traffic.json", "r01_sweep_traffic.json"):
+        tfile = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tfile):
+            tj = json.load(open(tfile))
+            if tj.get("batch") == B and tj.get("mc_steps") == S and tj.get("n", 29) == n:
+                traffic = tj.get("dram_bytes_per_launch")
+                break
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+    wsup = n in (9, 13, 21, 25, 29)
+    kname = ("wsweep_kernel<%d, %d>" % (n, 0 if B > 444 else (4 if B > 148 else 8))) if (wsup and B > 64 and not (n <= 16 and 444 < B <= 768)) \
+        else "sweep_kernel<%d>" % max(2, (n + 7) // 8)
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
-    xh = torch.as_tensor(x_host).pin_memory()
-    sih = torch.as_tensor(si_host).pin_memory()
+    xh = torch.as_tensor(x_host_all[:B]).pin_memory()
+    sih = torch.as_tensor(si_host_all[:B]).pin_memory()
     xo = torch.empty_like(xh).pin_memory()
     Vo = torch.empty(B, dtype=torch.float64).pin_memory()
-    stats = torch.empty(3, dtype=torch.float64).pin_memory()
+    stats_h = torch.empty(8, dtype=torch.float64).pin_memory()
+    stats_d = torch.zeros(8, dtype=torch.float64, device=dev)
+    ekey = cg.device_key(5000 + rank)
 
-    def e2e_step(k):
+    def e2e_step():
         xd = xh.to(dev, non_blocking=True)
         sd = sih.to(dev, non_blocking=True)
-        _, xd, acc_, = cg.sample_x(5000 + k, sd, logp, xd, params, S, CFG["mc_stddev"], c["L"])
-        V = cg.potential_energy(xd, CFG["kappa"], G, c["L"], c["rs"]) + Vconst
-        vm_, v2_ = cg.potential_stats(V)
+        cg.mcmc(logp.bind(params, sd), xd, ekey, S, COMMON["mc_stddev"], wrap_L=c["L"], stats=stats_d, advance_key=True,
+                _want_rate=False)
+        V = cg.potential_energy(xd, COMMON["kappa"], G, c["L"], c["rs"], stats=stats_d)
+        if world > 1:
+            dist.all_reduce(stats_d[:5])
         xo.copy_(xd, non_blocking=True)
         Vo.copy_(V, non_blocking=True)
-        stats.copy_(torch.stack([acc_, vm_, v2_]), non_blocking=True)
-    for k in range(2):
-        e2e_step(k)
+        stats_h.copy_(stats_d, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ke = max(3, args.steps // 2)
     a.record()
-    for k in range(ke):
-        e2e_step(10 + k)
+    for _ in range(ke):
+        e2e_step()
     b.record()
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([a.elapsed_time(b) / ke], dtype=torch.float64, device=dev)
@@ -360,24 +436,26 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * S / (float(e2e_ms) * 1e-3)
     h2d = xh.numel() * 8 + sih.numel() * 4
-    d2h = xo.numel() * 8 + Vo.numel() * 8 + 3 * 8
+    d2h = xo.numel() * 8 + Vo.numel() * 8 + 8 * 8
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (f64 I/O, range reduction, log-det sums and Metropolis test)", "data": "synthetic",
-        "config": make_config(B, world),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32 (f64 I/O, range reduction, single-particle stream, log-det sums and Metropolis test)", "data": "synthetic",
+        "config": make_config(ckey, cfg, B, world, args.scaling),
+        other_mode: other,
         "ewald_evals_per_sec": world * B / (ms_ewald * 1e-3),
         "sweep_kernel_ms": ms_sweep, "ewald_kernel_ms": ms_ewald, "ewald_timing": ew_mode,
         "ewald_roofline": {"bound": "fp32", "achieved": cg.flops.flop_ewald(n) * B / (ms_ewald * 1e-3) / 1e12, "peak": ffma,
                            "unit": "TFLOP/s", "frac": cg.flops.flop_ewald(n) * B / (ms_ewald * 1e-3) / 1e12 / ffma,
                            "kernel": "ewald_kernel"},
-        "accept_rate": float(acc), "V_mean_over_rs2": float(vm) / c["rs"] ** 2,
+        "accept_rate": acc_rate, "V_mean_over_rs2": v_mean / c["rs"] ** 2,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 4 * args.steps,      # per step: prep_wconst + wqueue_init + wsweep_kernel<29> + ewald_kernel
+        "gpu_launches": 3 * args.steps,      # per step: wsweep_prologue (or prep_params) + sweep kernel + ewald_kernel (+ 1 memcpy node, + NCCL)
+        "step_mode": "eager launches" if args.no_graph else "CUDA graph replay (3 kernels + constant-bank memcpy%s)" % (" + NCCL all-reduce" if world > 1 else ""),
         "clocks": clocks,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
-                     "traffic": traffic, "kernel": "wsweep_kernel<29, %d>" % (0 if B > 444 else (4 if B > 148 else 8)),
+                     "traffic": traffic, "kernel": kname,
                      "note": "compute-bound path (>2000 FLOP/B): achieved = (8n^3+895n^2+1760n)*(mc_steps+1)*B algorithmic "
                              "FLOP / CUDA-event kernel time; peak = FFMA-saturating micro-kernel measured in this run "
                              "(%s); MUFU peak %.2f Top/s"
@@ -385,17 +463,30 @@ def main():
                                 "MEASURED_PEAKS.json absent on this box; it holds only HBM and bf16 peaks anyway", mufu)},
         "wall_s_timed_region": t_wall,
         "van_sampler": van_info,
-        "reference_shard": shard_info,
     }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # ---- parity at the benchmarked shape + CPU baseline, one oracle run serves both: the benchmarked kernel (library's
+        # own choice at this batch) with explicit noise on all B walkers vs the float64 oracle on the first `walkers` of them
+        threads = os.cpu_count() or 1
+        walkers = min(CPU_SAMPLE_WALKERS[n], B)
+        rng = np.random.default_rng(44)
+        noise, unif = rng.standard_normal((S, B, n, 2)), rng.random((S, B))
+        x0 = x_host_all[:B].copy()
+        xg, accg, trg = cg.mcmc(bound, x0.copy(), cg.ExplicitNoise(noise, unif), S, COMMON["mc_stddev"], return_trace=True)
+        tro, xor_, Vor, t_sweep, t_ew = oracle_sample(c, x0, si_host_all[:B], noise, unif, walkers, threads)
+        line["parity"] = parity_report(trg, tro, unif, walkers)
+        line["parity"]["kernel"] = kname
+        Vg = cg.potential_energy(xor_ - c["L"] * np.floor(xor_ / c["L"]), COMMON["kappa"], G, c["L"], c["rs"])
+        line["parity"]["max_rel_ewald_err"] = float(np.max(np.abs(Vg - Vor)) / np.max(np.abs(Vor)))
+        line["accept_mismatch_frac"] = line["parity"]["accept_mismatch_frac"]
+        line["max_rel_logp_err"] = line["parity"]["max_rel_logp_err"]
+        v = walkers * S / (t_sweep + t_ew)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d walkers x full step (50 proposals + initial log p + Ewald): restated reference "
+                                          "algorithm (torch-f64 vmap+jacfwd+LAPACK), %.1f s; the same run is the parity check"
+                                          % (walkers, t_sweep + t_ew),
+                                "ewald_evals_per_sec": walkers / t_ew}
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            from oracle import tables
-            v, ew, secs = cpu_reference_rate(c, x_host, si_host, tables.kpoints(2, CFG["Gmax"]), 256, 7, threads)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "256 walkers x (7 proposals + initial log p) + Ewald, scaled to the 50-proposal "
-                                              "sweep; restated reference algorithm (torch-f64 vmap+jacfwd+LAPACK), %.1f s" % secs,
-                                    "ewald_evals_per_sec": ew}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
