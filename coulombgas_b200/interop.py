@@ -54,24 +54,30 @@ def sp_orbitals(dim, Emax=60, kind=None):
     return lat[perm], e[perm]
 
 
-def twist_sort(indices, twist, kind=None):
-    """src/orbitals.py:46-55 -> (indices + twist re-sorted by twisted energy, twisted energies).  `kind`: see sp_orbitals."""
+def twist_sort(indices, twist, kind="stable"):
+    """src/orbitals.py:46-55 -> (indices + twist re-sorted by twisted energy, twisted energies).
+
+    The reference calls this with `twist = jnp.array(args.twist)` (main.py:72,88): `indices + twist` is then a jax array and
+    `Es_twist.argsort()` is jnp.argsort, which is STABLE -- unlike the first sort in sp_orbitals, which acts on a NumPy array.
+    Hence kind="stable" by default here; kind=None gives NumPy's default (unstable) sort, which is what a caller passing a
+    NumPy twist to the reference's function gets (the committed fixtures were generated that way, tools/make_golden.py)."""
     kt = np.asarray(indices) + np.asarray(twist, dtype=np.float64)
     e = np.sum(kt * kt, axis=1)
     perm = e.argsort(kind=kind)
     return kt[perm], e[perm]
 
 
-def sp_indices_twist(dim, Emax, twist, kind=None, order=None):
+def sp_indices_twist(dim, Emax, twist, kind=None, order=None, kind_twist="stable"):
     """main.py:79-90: the (M, dim) float64 k-table the kernels take as `ktable`, DESCENDING twisted energy
-    (row M-1 is the lowest orbital; the ground state occupies rows M-n..M-1, main.py:101).
+    (row M-1 is the lowest orbital; the ground state occupies rows M-n..M-1, main.py:101).  `kind`: sort of sp_orbitals
+    (NumPy default, as in the reference); `kind_twist`: sort of twist_sort (stable, as jnp.argsort in a real reference run).
 
     order="shipped": the table with the order of degenerate orbitals the reference's SHIPPED runs (data/, twist
     (1/4, 1/4), Emax 25 / 36 / 49) were trained with, recovered by tools/recover_tie_order.py from the exact free-fermion
     answer of the shipped pretraining runs.  Use it to replay shipped checkpoints: with today's NumPy order
     the shipped VAN parameters are off by up to 13 in log p (n = 57)."""
     idx, _ = sp_orbitals(dim, Emax, kind)
-    kt, e = twist_sort(idx, twist, kind)
+    kt, e = twist_sort(idx, twist, kind_twist)
     kt, e = np.ascontiguousarray(kt[::-1], dtype=np.float64), np.ascontiguousarray(e[::-1], dtype=np.float64)
     if order is None:
         return kt, e
@@ -159,14 +165,15 @@ def pretrained_model_filename(freefermion_path):
 
 
 class _Opaque(tuple):
-    """Stand-in for pickled objects of libraries that are not installed (optax optimiser states, haiku containers):
-    kept as an empty tuple so the dict round-trips; the hot path never looks inside `opt_state`."""
+    """Stand-in for pickled objects of libraries that are not installed (optax optimiser states): kept as an empty tuple
+    subclass so that the dict loads; the hot path never looks inside `opt_state`.  save_data refuses to write one (the
+    re-saved checkpoint could not be resumed by the reference's optimiser): pass a real opt_state or drop the key."""
 
     def __new__(cls, *a, **k):
         return super().__new__(cls)
 
-    def __reduce__(self):
-        return (tuple, ())
+    def __setstate__(self, state):
+        pass
 
 
 def _rebuild_jax_array(fun, args, arr_state, aval_state=None):
@@ -176,14 +183,38 @@ def _rebuild_jax_array(fun, args, arr_state, aval_state=None):
     return arr
 
 
+def _flat_mapping(*args, **kwargs):
+    """haiku's FlatMapping (immutable dict of parameters) -> plain dict."""
+    if args and isinstance(args[0], dict):
+        return dict(args[0], **kwargs)
+    return dict(*args, **kwargs)
+
+
+# what a reference checkpoint legitimately contains: numpy arrays / scalars / dtypes and plain containers.  Everything else
+# is refused -- unpickling must not be able to import arbitrary callables (a pickle is code).
+_SAFE = {
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+    ("collections", "OrderedDict"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"),
+    ("builtins", "frozenset"), ("builtins", "complex"), ("builtins", "slice"), ("builtins", "bytearray"),
+}
+
+
 class _RefUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         root = module.split(".")[0]
-        if root == "jax" or root == "jaxlib":
+        if root in ("jax", "jaxlib"):
             return _rebuild_jax_array if name == "_reconstruct_array" else _Opaque
+        if root == "haiku" and name == "FlatMapping":
+            return _flat_mapping
         if root in ("optax", "haiku", "flax", "chex"):
             return _Opaque
-        return super().find_class(module, name)
+        if (module, name) in _SAFE:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError("refusing to unpickle %s.%s: not part of a CoulombGas checkpoint "
+                                     "(numpy arrays, plain containers, jax/optax/haiku stand-ins)" % (module, name))
 
 
 def _numpyfy(t):
@@ -214,6 +245,9 @@ def save_data(data, filename):
     """src/checkpoint.py:15-17.  Arrays are written as numpy (torch tensors are moved to host first), which the
     reference's `pickle.load` + `src.shard` / `src.replicate` accept unchanged (main.py:218-223)."""
     def host(t):
+        if isinstance(t, _Opaque):
+            raise ValueError("save_data: the object holds a placeholder for a pickled optax/haiku object that was dropped on "
+                             "load (e.g. opt_state): pass the real object, an empty tuple, or remove the key explicitly")
         if isinstance(t, dict):
             return {k: host(v) for k, v in t.items()}
         if type(t) in (list, tuple):

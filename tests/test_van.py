@@ -173,7 +173,8 @@ def test_kernel_entropy_matches_shipped_logs(cg):
         c = load_van(tag)          # the jointly trained VAN of a shipped interacting run (not used by the tie-order recovery)
         S = {}
         for order in (None, "shipped"):
-            kt, _ = interop.sp_indices_twist(2, Emax, (0.25, 0.25), order=order)
+            # order None: "today's NumPy" table (both sorts NumPy's default argsort, as tools/make_golden*.py produced it)
+            kt, _ = interop.sp_indices_twist(2, Emax, (0.25, 0.25), order=order, kind_twist=None if order is None else "stable")
             sampler, _ = cg.make_autoregressive_sampler(kt, c["n"], c["M"])
             _, lp = sampler(c["params"], 7, 32768, return_log_prob=True)
             S[order] = float(-lp.mean())

@@ -136,9 +136,9 @@ def main():
     ref_case("n29_rs10", 29, 2, 25, 10.0, d["params_flow"], d["x"][0][:64], n_logpsi=8, n_mc=0)
     # C4 / C5
     d = ckpt("n_49_dim_2_rs_0.5_*")
-    ref_case("n49_rs0.5", 49, 2, 36, 0.5, d["params_flow"], d["x"][0], n_logpsi=6, n_mc=2, mc_steps=3)
+    ref_case("n49_rs0.5", 49, 2, 36, 0.5, d["params_flow"], d["x"][0], n_logpsi=6, n_mc=16, mc_steps=10)
     d = ckpt("n_57_dim_2_rs_0.25_*")
-    ref_case("n57_rs0.25", 57, 2, 49, 0.25, d["params_flow"], d["x"][0], n_logpsi=6, n_mc=2, mc_steps=3)
+    ref_case("n57_rs0.25", 57, 2, 49, 0.25, d["params_flow"], d["x"][0], n_logpsi=6, n_mc=16, mc_steps=10)
     # C1/C2: n=13 — no shipped flow checkpoint; haiku init (RandomNormal(0.01), zero bias) via the
     # stand-in, scaled up x30 so the flow is not a near-identity, walkers uniform in [0,L)
     n = 13
