@@ -12,7 +12,10 @@
 //   * the reciprocal sum is a small complex matrix product  S+-(gx,gy) = sum_i px_i[gx] py_i[gy]^(*)  over the
 //     (gmax+1)^2 quadrant, register-tiled 2 x 4 per lane: per particle 3 broadcast LDS.128 feed 32 FFMA; the
 //     merged weights (w+, w-) sit in a dense CTA-shared table (zero outside the |G| <= Gmax disc);
-//   * the n(n-1)/2 real-space pairs are dealt round-robin to the lanes (triangular index decoded per pair).
+//   * the n(n-1)/2 real-space pairs are dealt round-robin to the lanes (triangular index decoded per pair);
+//   * batches that cannot fill the GPU with one warp per walker (the named 2048-walker batch: 0.58 waves) give every walker
+//     TWO warps: the pair shares the walker's tables, splits the particles of the table build, the tiles and the pairs, and
+//     meets at a named barrier (64 threads) -- per-walker latency halves, 4096 warps fill the 148 SMs in one wave.
 #include "cgb_common.cuh"
 #include "cgb_internal.h"
 
@@ -35,9 +38,21 @@ __device__ __forceinline__ float2 cmulf(const float2 a, const float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+#ifndef CGBE_WPW2_MAX_BATCH_PER_SM
+#define CGBE_WPW2_MAX_BATCH_PER_SM 8       // two warps per walker while B <= this x #SMs (twice that for n > 32: two particles per lane)
+#endif
+
 __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_part[8];
     const int n = p.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int wpw = p.wpw;                                   // warps per walker: 1 or 2
+    const int grp = wpw == 2 ? warp >> 1 : warp, sub = wpw == 2 ? warp & 1 : 0, ngrp = nwarps / wpw;
+    const int glane = lane + 32 * sub, gsize = 32 * wpw;
+    auto group_sync = [&]() {
+        if (wpw == 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + grp) : "memory");
+        else __syncwarp();
+    };
     const EwLay L_(n, p.gmax);
     const int tiles_x = L_.npx >> 1, tiles_y = L_.npy >> 2, ntiles = tiles_x * tiles_y;
     // dense weights (w+, w-)[gx][gy] over the padded quadrant, CTA-shared
@@ -50,7 +65,7 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
         Wd[(int)it.x * L_.npy + (int)it.y] = make_float2(0.5f * it.z, 0.5f * it.w);
     }
     __syncthreads();
-    unsigned char* const sm = smem_raw + wd_bytes + warp * L_.total;
+    unsigned char* const sm = smem_raw + wd_bytes + grp * L_.total;
     double2* const u = reinterpret_cast<double2*>(sm);
     float2* const px = reinterpret_cast<float2*>(sm + L_.o_px);
     float2* const py = reinterpret_cast<float2*>(sm + L_.o_py);
@@ -59,10 +74,12 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
     const int npairs = n * (n - 1) / 2;
     const float tn1 = (float)(2 * n - 1);
 
-    for (int b = blockIdx.x * nwarps + warp; b < p.B; b += gridDim.x * nwarps) {
-        __syncwarp();
+    for (int b0 = blockIdx.x * ngrp; b0 < p.B; b0 += gridDim.x * ngrp) {      // the same trip count for every warp of the CTA
+        const int b = b0 + grp;
+        const bool live = b < p.B;
+        group_sync();
         // ---- reduced coordinates and power tables e^{2 pi i g u}, g = 0..gmax (padding harmonics = 0)
-        for (int i = lane; i < n; i += 32) {
+        for (int i = glane; live && i < n; i += gsize) {
             double2 xv = __ldg(reinterpret_cast<const double2*>(p.x) + (size_t)b * n + i);
             xv.x *= invL; xv.y *= invL;                                   // x / L  (potential.py:77)
             xv.x -= floor(xv.x); xv.y -= floor(xv.y);
@@ -87,10 +104,10 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
                 }
             }
         }
-        __syncwarp();
+        group_sync();
         float acc = 0.f;
         // ---- reciprocal space: 2 x 4 register tile of (gx, gy) per lane
-        for (int tile = lane; tile < ntiles; tile += 32) {
+        for (int tile = glane; live && tile < ntiles; tile += gsize) {
             const int tx = tile / tiles_y, ty = tile - tx * tiles_y;
             const float4* pxa = reinterpret_cast<const float4*>(px + 2 * tx);
             const float4* pya = reinterpret_cast<const float4*>(py + 4 * ty);
@@ -125,7 +142,7 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
                 }
         }
         // ---- real space, nearest image (potential.py:45-50): pair index q -> (i < j), row i starts at i(2n-1-i)/2
-        for (int q = lane; q < npairs; q += 32) {
+        for (int q = glane; live && q < npairs; q += gsize) {
             int i = (int)((tn1 - sqrtf(fmaf(tn1, tn1, -8.f * (float)q))) * 0.5f);
             i = max(0, min(i, n - 2));
             int r0 = (i * (2 * n - 1 - i)) >> 1;
@@ -144,7 +161,12 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
         double a = (double)acc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) {
+        if (wpw == 2) {                                   // the second warp hands its partial sum to the first (fixed order)
+            if (sub == 1 && lane == 0) s_part[grp] = a;
+            group_sync();
+            if (sub == 0) a += s_part[grp];
+        }
+        if (lane == 0 && sub == 0 && live) {
             const double g0 = -2.0 * sqrt(3.14159265358979323846) / p.kappa;       // potential.py:59
             a += g0 * (0.5 * n * (n - 1));                                        // potential.py:62
             p.out[b] = 2.0 * p.rs * invL * a;                                     // potential.py:77
@@ -186,12 +208,18 @@ int launch_ewald(const EwaldParams& p, cudaStream_t st) {
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // warps per CTA: 8 while three CTAs still fit one SM's shared memory, fewer for large n / gmax; small batches
-    // use smaller CTAs so that the walkers spread over all SMs
-    int wpc = 8;
-    while (wpc > 1 && (size_t)wd_bytes + (size_t)wpc * L_.total > 72 * 1024) wpc >>= 1;
-    while (wpc > 1 && (long long)p.B < (long long)sms * wpc) wpc >>= 1;
-    const size_t smem = (size_t)wd_bytes + (size_t)wpc * L_.total;
+    // two warps per walker while one warp per walker cannot fill the machine (see the header of this file)
+    EwaldParams q = p;
+    // measured (profiles/r02_time_ewald.txt): n=29: B=256 6.2 vs 8.2 us, B=2048 14.2 vs 11.7 us (the second half-wave costs more
+    // than the shorter chains save); n=57: B=512 12.5 vs 18.3 us, B=2048 29.8 vs 39.3 us
+    q.wpw = (long long)p.B <= (long long)CGBE_WPW2_MAX_BATCH_PER_SM * (p.n > 32 ? 2 : 1) * sms ? 2 : 1;
+    // walkers per CTA: 8 (4 with two warps each) while three CTAs still fit one SM's shared memory, fewer for large n / gmax;
+    // small batches use smaller CTAs so that the walkers spread over all SMs
+    int gpc = 8 / q.wpw;
+    while (gpc > 1 && (size_t)wd_bytes + (size_t)gpc * L_.total > 72 * 1024) gpc >>= 1;
+    while (gpc > 1 && (long long)p.B < (long long)sms * gpc) gpc >>= 1;
+    const int wpc = gpc * q.wpw;
+    const size_t smem = (size_t)wd_bytes + (size_t)gpc * L_.total;
     if (smem > 227 * 1024) return CGB_E_UNSUPPORTED;
     // attribute + occupancy queries are cached per (device, shape): the steady-state call is one launch
     static thread_local struct { int dev; size_t smem; int wpc; int occ; } cache = {-1, 0, 0, 0};
@@ -203,9 +231,9 @@ int launch_ewald(const EwaldParams& p, cudaStream_t st) {
         cache = {dev, smem, wpc, occ};
     }
     occ = cache.occ;
-    const long long need = ((long long)p.B + wpc - 1) / wpc;
+    const long long need = ((long long)p.B + gpc - 1) / gpc;
     const int grid = (int)(need < (long long)sms * occ ? need : (long long)sms * occ);
-    ewald_kernel<<<grid, wpc * 32, smem, st>>>(p);
+    ewald_kernel<<<grid, wpc * 32, smem, st>>>(q);
     return (int)cudaGetLastError();
 }
 

@@ -91,6 +91,7 @@ struct EwaldParams {
     const double* x; int B, n; double L, rs, kappa;
     const float4* items; int n_items, gmax;
     double* out;
+    int wpw;                      // warps per walker (1 or 2), chosen by launch_ewald
     double* stats;                // CGB_STATS_LEN doubles or null: [2] sum V, [3] sum V^2, [4] B; [7] scratch counter
 };
 int launch_ewald(const EwaldParams& p, cudaStream_t st);
