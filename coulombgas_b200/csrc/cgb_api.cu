@@ -95,6 +95,7 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     if ((uintptr_t)params & 15) return CGB_E_BADARG;            // float64 parameters are read as 16-byte pairs
     cudaStream_t st = (cudaStream_t)stream;
     SweepParams p;
+    p.n_sms = 148;
     p.x = x; p.x_out = x_out; p.state_idx = state_idx; p.ktable = ktable; p.M = M;
     p.tw0 = twist[0]; p.tw1 = twist[1]; p.wpack = (const float*)workspace; p.params = params;
     p.noise = noise; p.uniforms = uniforms; p.seed = seed; p.key_dev = key_dev; p.mc_steps = mc_steps; p.sigma = sigma;

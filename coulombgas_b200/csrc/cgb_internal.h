@@ -60,6 +60,7 @@ struct SweepParams {
     int* ws_nacc;                 // (B) accepted moves so far
     int cspec;                    // CTA kernel's speculative mode: -1 = auto (widest tree that fits), 0 = off, 4/8 = CTAs per walker
     unsigned long long* prof;     // developer builds (CGBW_PROF): 12 per-phase cycle sums in the workspace, else unused
+    unsigned n_sms;               // multiprocessors of the device (CTA i starts on SM i % n_sms)
     int spec;                     // 4 / 8: speculative mode, warps per walker (one CTA evaluates the next 2-3 / 3-4 steps' proposals at once)
 };
 

@@ -221,6 +221,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 #ifndef CGBW_FIXSUM
 #define CGBW_FIXSUM 1       // pass 1: sum_k |a_k| and sum_k d_k in 32-bit fixed point (FADD with a magic constant + IADD) instead of
 #endif                      // F2F + DADD per term (the conversions run on the quarter-rate XU pipe); trig feature sums separable
+#ifndef CGBW_STAGGER_NS
+#define CGBW_STAGGER_NS 0   // ready-queue kernel: start delay between the co-resident CTAs of an SM (0 = none)
+#endif
 #ifndef CGBW_WPC
 #define CGBW_WPC 4          // warps per CTA of the ready-queue kernel (12 / CGBW_WPC CTAs per SM)
 #endif
@@ -581,6 +584,14 @@ wsweep_kernel(const SweepParams p) {
 
 #if CGBW_PROF
     if (lane == 0) s_prof_t0[threadIdx.x >> 5] = clock64();
+#endif
+#if CGBW_STAGGER_NS
+    // the co-resident CTAs of an SM (round-robin placement: CTA i on SM i % #SMs) start their first evaluation a third of an
+    // evaluation apart, so that their phases (and with them the XU / FP64 pipe demand) are out of step from the beginning
+    if constexpr (!SPEC) {
+        const unsigned wave = blockIdx.x / p.n_sms;
+        for (unsigned w = 0; w < wave; ++w) __nanosleep(CGBW_STAGGER_NS);
+    }
 #endif
     for (;;) {
         int b = 0, step = 0;
@@ -1597,10 +1608,12 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     static thread_local WLaunchCfg cq[CGBW_WPC + 1];
     WLaunchCfg& c = cq[wpc];
     if (const int rc = config(wsweep_kernel<N, 0>, wpc, c)) return rc;
+    SweepParams pq = p;
+    pq.n_sms = (unsigned)sms;
     long long grid = (long long)sms * c.occ;
     const long long need = ((long long)p.B + wpc - 1) / wpc;      // never more warps than walkers
     if (grid > need) grid = need;
-    wsweep_kernel<N, 0><<<(int)grid, wpc * 32, c.smem, st>>>(p);
+    wsweep_kernel<N, 0><<<(int)grid, wpc * 32, c.smem, st>>>(pq);
     return (int)cudaGetLastError();
 }
 
