@@ -1581,10 +1581,13 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     static thread_local int sms_cache[2] = {-1, 0};
     if (sms_cache[0] != dev) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); sms_cache[0] = dev; sms_cache[1] = sms; }
     sms = sms_cache[1];
-    auto config = [&](auto kern, const int nw, WLaunchCfg& c) -> int {
+    auto config = [&](auto kern, const int nw, const int nw_max, WLaunchCfg& c) -> int {
         if (c.dev == dev && c.wpc == nw) return 0;
         const size_t smem = (size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * nw;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // the attribute belongs to the FUNCTION, not to a launch shape: always the largest CTA this instantiation is launched with
+        // (a smaller value set for a 2-warp launch would make the next 4-warp launch fail with cudaErrorInvalidValue)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((size_t)W_SHARED_BYTES + (size_t)WLay<N>::total * nw_max));
         if (e != cudaSuccess) return (int)e;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nw * 32, smem);
@@ -1593,7 +1596,7 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     };
     if (p.spec) {          // speculative mode: one CTA of 8 (B <= #SMs) or 4 warps per walker, persistent over the sweep
         auto go = [&](auto kern, const int nw, WLaunchCfg& c) -> int {
-            if (const int rc = config(kern, nw, c)) return rc;
+            if (const int rc = config(kern, nw, nw, c)) return rc;
             long long grid = (long long)sms * c.occ;
             if (grid > (long long)p.B) grid = p.B;
             kern<<<(int)grid, nw * 32, c.smem, st>>>(p);
@@ -1607,7 +1610,7 @@ static int launch_wn(const SweepParams& p, cudaStream_t st) {
     while (wpc > 1 && (long long)p.B < (long long)sms * 3 * wpc) wpc >>= 1;
     static thread_local WLaunchCfg cq[CGBW_WPC + 1];
     WLaunchCfg& c = cq[wpc];
-    if (const int rc = config(wsweep_kernel<N, 0>, wpc, c)) return rc;
+    if (const int rc = config(wsweep_kernel<N, 0>, wpc, CGBW_WPC, c)) return rc;
     SweepParams pq = p;
     pq.n_sms = (unsigned)sms;
     long long grid = (long long)sms * c.occ;

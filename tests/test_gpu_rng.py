@@ -136,6 +136,27 @@ def test_two_streams_two_parameter_sets(cg, cases):
         cg.set_sweep_kernel(None)
 
 
+def test_alternating_batch_sizes_one_process(cg, cases):
+    """Launch configurations are cached per kernel instantiation; the dynamic-shared-memory attribute belongs to the function,
+    not to the launch shape: a small batch (2 warps per CTA) between two large ones (4 warps per CTA) must not shrink it."""
+    c = cases("n29_rs1")
+    cg.set_sweep_kernel("warp")
+    try:
+        logp = cg.make_logp(c["ktable"], c["L"])
+        ref = {}
+        for B in (2048, 1000, 2048, 300, 2048, 1000):
+            reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+            x = torch.as_tensor(np.tile(c["x"], (reps, 1, 1))[:B], device="cuda")
+            si = torch.as_tensor(np.tile(c["state_idx"], (reps, 1))[:B], device="cuda")
+            xo, acc = cg.mcmc(logp.bind(c["params"], si), x.clone(), 11, 4, 0.1)
+            torch.cuda.synchronize()
+            if B in ref:
+                assert torch.equal(xo, ref[B])
+            ref[B] = xo
+    finally:
+        cg.set_sweep_kernel(None)
+
+
 def test_argument_validation_precedes_the_launch(cg, cases):
     """mcmc() must reject a wrong wrap_L / shape BEFORE the kernel advances the donated walker buffer."""
     c = cases("n13_rs10")
