@@ -489,7 +489,16 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Orderly exit: CUDA graphs that hold NCCL kernels must be gone before the communicator is torn down (a
+        # destroy_process_group() with live captured collectives was observed to hang); after the last barrier every rank has
+        # finished its work, so the processes leave without the teardown handshake.
+        step.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

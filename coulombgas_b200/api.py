@@ -158,9 +158,10 @@ class Logp:
         nbytes = ctypes.c_size_t()
         check(lib.cgb_logp_workspace_bytes(B, n, ctypes.byref(nbytes)), "cgb_logp_workspace_bytes")
         if d not in self._ws or self._ws[d].numel() < nbytes.value:      # grows with the batch (per-walker scheduler state)
-            fb = self.fallback_count()
-            self._ws[d] = torch.zeros(nbytes.value, dtype=torch.uint8, device=_dev())
-            self._ws[d][4096:4104].view(torch.int64).fill_(fb)            # the fallback counter is cumulative
+            new = torch.zeros(nbytes.value, dtype=torch.uint8, device=_dev())
+            if d in self._ws:
+                new[4096:4112].copy_(self._ws[d][4096:4112])              # the fallback counters are cumulative (device-side copy:
+            self._ws[d] = new                                             # no host sync, legal under graph capture)
         return self._ws[d]
 
     def fallback_count(self):
@@ -170,6 +171,14 @@ class Logp:
         if d not in self._ws:
             return 0
         return int(self._ws[d][4096:4104].view(torch.int64).item())
+
+    def slater_fallback_count(self):
+        """Cumulative number of evaluations (warp kernel) whose FP32 Slater LU exceeded its error indicator, or whose wave
+        vectors exceed the power tables, and that were redone by the float64 LU."""
+        d = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        if d not in self._ws:
+            return 0
+        return int(self._ws[d][4104:4112].view(torch.int64).item())
 
     def __call__(self, x, params, state_idx, return_parts=False, return_jac=False):
         xd, was_np = _to_dev(x, torch.float64)
