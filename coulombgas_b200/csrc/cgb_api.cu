@@ -109,6 +109,7 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     char* ws = (char*)workspace;
     p.fallback_counter = (unsigned long long*)(ws + WS_CTR);
     p.wconst = ws + WS_WCONST;
+    p.wshared = (const double*)(ws + WS_WSHARED);
     p.qctr = (unsigned long long*)(ws + WS_CTR + 64);
     p.prof = (unsigned long long*)(ws + WS_CTR + 128);
     p.qcap = ws_qcap(B);

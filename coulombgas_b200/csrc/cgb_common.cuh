@@ -52,6 +52,30 @@ __device__ __forceinline__ void softplus_sigmoid(float pre, float& sp, float& sg
     sg = a >= 0.f ? r : e * r;
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous block global -> shared, completion on an mbarrier.
+// Called by EVERY thread of the CTA (contains two block barriers); thread 0 arms the barrier with the byte count and issues the
+// copy, everybody waits on the phase-0 parity.  dst / src 16-byte aligned, bytes a multiple of 16; `mbar` is 8 bytes of shared
+// memory that nobody else touches.  The weight blocks of the sweep kernels (a few kB, staged once per CTA) come in this way.
+__device__ __forceinline__ void tma_stage_block(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* mbar) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar), dst = (unsigned)__cvta_generic_to_shared(dst_smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(mb) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb) : "memory");
+    }
+    __syncthreads();
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG for the throughput mode --------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -52,6 +52,7 @@ struct SweepParams {
     unsigned long long* fallback_counter;   // evaluations redone with the pivoted LU (in the workspace)
     // ---- warp-per-walker kernel only (cgb_wsweep.cu): per-call scheduler state in the caller's workspace
     const void* wconst;           // staging copy of the constant-bank weight block (device)
+    const double* wshared;        // float64 weights of the single-particle stream in the CTA-shared layout (TMA source, 16-byte aligned)
     unsigned long long* qctr;     // [0] queue head, [1] queue tail, [2] spin diagnostics (initialised per call)
     unsigned long long* queue;    // (qcap) ready-queue slots
     unsigned qcap;                // power of two >= 2*B
@@ -70,7 +71,8 @@ enum : size_t {
     WS_CTR = 4096,          // +0: pivot-fallback counter (u64, cumulative); +8: float64-Slater-fallback counter; +64: queue head, tail, spin diagnostics (3 x u64);
                             // +128: 12 x u64 per-phase cycle sums (developer builds with CGBW_PROF only)
     WS_WCONST = 4352,       // staging copy of the constant-bank weight block (warp-per-walker kernel)
-    WS_DYN = 4352 + 11264
+    WS_WSHARED = 4352 + 11264,   // float64 single-particle weights in the CTA-shared layout: source of the kernel's TMA bulk copy
+    WS_DYN = 4352 + 11264 + 5120
 };
 inline unsigned ws_qcap(int B) { unsigned c = 64; while (c < 2u * (unsigned)(B > 0 ? B : 1)) c <<= 1; return c; }
 inline size_t ws_round(size_t b) { return (b + 255) & ~size_t(255); }

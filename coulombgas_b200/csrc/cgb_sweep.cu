@@ -218,8 +218,11 @@ sweep_kernel(const SweepParams p) {
     const double invL = 1.0 / p.L;
     const float alpha = (float)(2.0 * 3.14159265358979323846 * invL) * invn;   // (2 pi / L) / n
 
-    for (int t = tid; t < W_TOTAL / 4; t += NW * 32)
-        reinterpret_cast<float4*>(s.wts)[t] = reinterpret_cast<const float4*>(p.wpack)[t];
+    {   // FP32 weight pack (4 kB): one TMA bulk copy per CTA
+        __shared__ __align__(8) unsigned long long s_mbar;
+        static_assert((4 * W_TOTAL) % 16 == 0, "bulk copies move multiples of 16 bytes");
+        tma_stage_block(s.wts, p.wpack, 4 * W_TOTAL, &s_mbar);
+    }
     const float4* wt4 = reinterpret_cast<const float4*>(s.wts + W_WT);     // [f*4+cq]
     const float4* bt4 = reinterpret_cast<const float4*>(s.wts + W_BT);
     const float4* w0c4 = reinterpret_cast<const float4*>(s.wts + W_W0C);   // [f*4+cq]

@@ -60,7 +60,18 @@ __constant__ WConst cW;
 
 // Prologue of a sweep, ONE launch: weight block, ready queue (all walkers ready for step 0), per-walker step counters,
 // statistics vector, device key advance.
-__global__ void wsweep_prologue_kernel(const double* __restrict__ p, WConst* __restrict__ w, unsigned long long* slots,
+// ---------------------------------------------------------------------------------------------------
+// CTA-shared float64 weights of the forward single-particle stream, regrouped [c4][e][kk] (output channel c = 4 c4 + kk)
+// so that one group of 4 output channels reads contiguous 32-byte rows by broadcast LDS.128.  (As runtime-indexed
+// constant-bank loads these 8 kB thrashed the constant cache: 16 % of all stall samples on 2 % of the instructions.)
+struct WShared {
+    double w1a[4][16][4];
+    double w1c[4][16][4];
+    double w0c[4][5][4];
+};
+constexpr int W_SHARED_BYTES = ((sizeof(WShared) + 15) & ~15) + 128;      // + the speculative mode's log p exchange slots
+
+__global__ void wsweep_prologue_kernel(const double* __restrict__ p, WConst* __restrict__ w, double* __restrict__ wsh, unsigned long long* slots,
                                        unsigned cap, unsigned B, unsigned long long* ctr, int* done, double* stats, double nprop,
                                        uint32_t* key_dev, int advance_key) {
     {   // ready queue (bounded MPMC, Vyukov style): slot = (sequence << 32) | walker.  Slot i starts "filled" with walker i
@@ -78,6 +89,19 @@ __global__ void wsweep_prologue_kernel(const double* __restrict__ p, WConst* __r
         }
     }
     if (blockIdx.x != 0) return;
+    {   // float64 weights of the single-particle stream in the layout the sweep kernel's CTAs fetch by one TMA bulk copy
+        constexpr int S_W0 = 96, S_W1 = 256;
+        WShared* const sh = reinterpret_cast<WShared*>(wsh);
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+            const int e = t >> 4, c = t & 15;
+            sh->w1a[c >> 2][e][c & 3] = p[S_W1 + t];                 // W1[e][c]        (acts on h_i)
+            sh->w1c[c >> 2][e][c & 3] = p[S_W1 + 512 + t];           // W1[32 + e][c]   (acts on mean_j t_ij)
+        }
+        for (int t = threadIdx.x; t < 80; t += blockDim.x) {
+            const int f = t >> 4, c = t & 15;
+            sh->w0c[c >> 2][f][c & 3] = p[S_W0 + 64 + t];            // W0[4 + f][c]
+        }
+    }
     // source offsets in the flat 1074 vector (include/cgb200.h)
     constexpr int S_WT = 0, S_BT = 80, S_W0 = 96, S_B0 = 240, S_W1 = 256, S_B1 = 1024, S_WF = 1040;
     constexpr double LOG2E = 1.4426950408889634;
@@ -314,17 +338,6 @@ __device__ __noinline__ float pivoted_lu_smem(float* Jf, int lane) {
     return mylog;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// CTA-shared float64 weights of the forward single-particle stream, regrouped [c4][e][kk] (output channel c = 4 c4 + kk)
-// so that one group of 4 output channels reads contiguous 32-byte rows by broadcast LDS.128.  (As runtime-indexed
-// constant-bank loads these 8 kB thrashed the constant cache: 16 % of all stall samples on 2 % of the instructions.)
-struct WShared {
-    double w1a[4][16][4];
-    double w1c[4][16][4];
-    double w0c[4][5][4];
-};
-constexpr int W_SHARED_BYTES = ((sizeof(WShared) + 15) & ~15) + 128;      // + the speculative mode's log p exchange slots
-
 // Float64 Slater log-determinant (fallback of the FP32 factorisation of the main kernel, and the path for wave vectors
 // beyond the power tables): row r = lane r, partially pivoted complex LU with implicit row exchange, register-resident,
 // shift-left (the active column is always register 0).  After its first update every unfinished row offers its new
@@ -512,19 +525,10 @@ wsweep_kernel(const SweepParams p) {
     // (a plain mov is still rematerialised by ptxas; the result of a shuffle is not)
     const int lane = __shfl_sync(0xffffffffu, (int)(threadIdx.x & 31), (int)(threadIdx.x & 31));
     const int wofs = __shfl_sync(0xffffffffu, (int)(W_SHARED_BYTES + (threadIdx.x >> 5) * L_::total), 0);
-    {
-        WShared* const sW = reinterpret_cast<WShared*>(smem_raw);
-        const WConst* wc = reinterpret_cast<const WConst*>(p.wconst);
-        for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-            const int e = t >> 4, c = t & 15;
-            sW->w1a[c >> 2][e][c & 3] = wc->dw1a[e][c];
-            sW->w1c[c >> 2][e][c & 3] = wc->dw1c[e][c];
-        }
-        for (int t = threadIdx.x; t < 80; t += blockDim.x) {
-            const int f = t >> 4, c = t & 15;
-            sW->w0c[c >> 2][f][c & 3] = wc->dw0c[f][c];
-        }
-        __syncthreads();                  // the only block barrier: before the warps go their own ways
+    {   // CTA-shared float64 weights: regrouped by the prologue kernel into the WShared layout, one TMA bulk copy per CTA
+        __shared__ __align__(8) unsigned long long s_mbar;
+        static_assert(sizeof(WShared) % 16 == 0, "bulk copies move multiples of 16 bytes");
+        tma_stage_block(smem_raw, p.wshared, (unsigned)sizeof(WShared), &s_mbar);   // (its barriers: before the warps go their own ways)
     }
     // the slice base as a pinned 32-bit shared-window address (the window base is a function of %cluster_ctarank that
     // the compiler otherwise re-derives with S2UR + ULEA at every use site)
@@ -747,9 +751,10 @@ wsweep_kernel(const SweepParams p) {
                                           ffma2s(f.c.y, make_float2(cW.wt[1][c], cW.wt[1][c + 1]),
                                           ffma2s(f.c.x, make_float2(cW.wt[0][c], cW.wt[0][c + 1]), make_float2(btr[c], btr[c + 1]))))));
                         sabi[c] += __float_as_uint(fabsf(a2.x) + cW.sabM[c]);
-                        P[c] = fmaf(P[c], ex2_approx(-fabsf(a2.x)), P[c]);
                         sabi[c + 1] += __float_as_uint(fabsf(a2.y) + cW.sabM[c + 1]);
-                        P[c + 1] = fmaf(P[c + 1], ex2_approx(-fabsf(a2.y)), P[c + 1]);
+                        const float2 e2 = make_float2(ex2_approx(-fabsf(a2.x)), ex2_approx(-fabsf(a2.y)));
+                        const float2 pp = __ffma2_rn(make_float2(P[c], P[c + 1]), e2, make_float2(P[c], P[c + 1]));    // P (1 + 2^-|a|), packed
+                        P[c] = pp.x; P[c + 1] = pp.y;
                     }
                 }
                 m0s[4] = (double)(int)(sdi - (unsigned)N * 0x40000000u) * (1.0 / 4194304.0);      // units of 2^-22
@@ -1644,7 +1649,8 @@ int launch_wsweep(const SweepParams& p, void* wconst_staging, cudaStream_t st) {
         else (void)cudaGetLastError();
     }
     const unsigned cap = p.spec ? 0u : (unsigned)p.qcap;
-    wsweep_prologue_kernel<<<cap ? (cap + 255) / 256 : 1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging), p.queue,
+    wsweep_prologue_kernel<<<cap ? (cap + 255) / 256 : 1, 256, 0, st>>>(p.params, reinterpret_cast<WConst*>(wconst_staging),
+                                                                       const_cast<double*>(p.wshared), p.queue,
                                                                        cap, (unsigned)p.B, p.qctr, p.done, p.out_stats,
                                                                        (double)p.B * (double)p.mc_steps,
                                                                        const_cast<uint32_t*>(p.key_dev), p.advance_key);

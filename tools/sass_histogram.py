@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """SASS opcode histogram per kernel of libcgb200.so (cuobjdump -sass): the repository's own evidence of what the kernels are
 made of -- packed FP32 FMAs (FFMA2 / FMUL2 / FADD2), float64 pipe (DFMA / DADD / DMUL), SFU (MUFU), warp collectives
-(SHFL / REDUX / CREDUX), cluster barriers (UCGABAR_ARV / UCGABAR_WAIT), spills (LDL / STL), and the absence of tensor-core /
-TMA instructions (UTC*MMA, UTMALDG: the contractions are K = 5/9/48, N = 16 and the tables are a few kB).
+(SHFL / REDUX / CREDUX), cluster barriers (UCGABAR_ARV / UCGABAR_WAIT), TMA bulk copies of the weight blocks (UBLKCP, with
+SYNCS mbarrier operations), spills (LDL / STL), and the absence of tensor-core instructions (UTC*MMA / HMMA: the contractions are
+K = 5/9/48, N = 16).
 usage: python tools/sass_histogram.py [lib.so] > profiles/r02_sass_histogram.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,7 +22,7 @@ for l in out.splitlines():
         hist[kern][m.group(1)] += 1
 WATCH = ["FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD", "DFMA", "DADD", "DMUL", "MUFU", "SHFL", "REDUX", "CREDUX", "LDS", "STS",
          "LDG", "STG", "ATOMG", "LDC", "LDCU", "LDL", "STL", "BAR", "UCGABAR_ARV", "UCGABAR_WAIT", "MEMBAR", "HMMA", "UTCHMMA", "UTMALDG",
-         "UBLKCP", "LDGSTS"]
+         "UBLKCP", "SYNCS", "LDGSTS"]
 print("# SASS opcode histogram of %s (static instruction counts per kernel)" % os.path.basename(lib))
 tot = collections.Counter()
 for k, h in hist.items():
