@@ -1,7 +1,5 @@
 set -x
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 400 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-timeout 120 python tools/time_sweep.py n29_rs1 2048 50 warp 2>&1 | tail -1
-timeout 120 python tools/time_sweep.py n29_rs1 8192 50 warp 5 2>&1 | tail -1
-timeout 120 python tools/time_sweep.py n57_rs0.25 512 50 auto 5 2>&1 | tail -1
-timeout 120 python tools/time_sweep.py n29_rs1 256 50 auto 2>&1 | tail -1
+for t in memcheck racecheck synccheck; do
+  timeout 600 compute-sanitizer --tool $t python tools/sanitize_small.py > gpurun_out/r02_san_$t.txt 2>&1
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize driver done" gpurun_out/r02_san_$t.txt | tail -2
+done

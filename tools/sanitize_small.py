@@ -17,8 +17,18 @@ for tag, B in (("n13_rs10", 3), ("n29_rs1", 3), ("n49_rs0.5", 2), ("n57_rs0.25",
     cg.set_sweep_kernel(None)
     cg.set_debug(force_pivot=True)
     lp2 = logp(x, c["params"], si)
-    cg.set_debug(force_pivot=False)
+    cg.set_debug(force_pivot=False, force_f64_slater=True)         # float64 Slater fallback of the warp kernel
+    cg.set_sweep_kernel("warp")
+    lp3 = logp(x, c["params"], si)
+    cg.set_debug(force_f64_slater=False)
+    cg.set_sweep_kernel(None)
     V = cg.potential_energy(x, c["kappa"], c["G"], c["L"], c["rs"])
+    # fused sampling step (prologue + sweep + Ewald with the statistics epilogue, device key), two-warps-per-walker Ewald
+    xd = torch.as_tensor(x, device="cuda")
+    st = cg.SamplingStep(logp, torch.as_tensor(si, device="cuda"), torch.as_tensor(cg.pack_params(c["params"]), device="cuda"),
+                         xd, 7, 3, 0.1, c["kappa"], cg.kpoints(2, 15), c["rs"], 0.0)
+    st.step(); print(tag, st.summary())
+    cg.debug_rng(3, 4, 2, c["n"], kat=np.zeros((2, 6), np.uint32))
     print(tag, lp[:2], lp2[:2], acc, V[:2])
 torch.cuda.synchronize()
 print("sanitize driver done")
