@@ -1,5 +1,3 @@
 set -x
-for t in memcheck racecheck synccheck; do
-  timeout 600 compute-sanitizer --tool $t python tools/sanitize_small.py > gpurun_out/r02_san_$t.txt 2>&1
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize driver done" gpurun_out/r02_san_$t.txt | tail -2
-done
+timeout 900 python tools/stress_spec.py 60 2>&1 | tail -3
+for i in 1 2 3; do timeout 400 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -1; done
