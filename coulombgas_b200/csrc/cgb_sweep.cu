@@ -285,7 +285,7 @@ sweep_kernel(const SweepParams p) {
           if (active)
           for (;;) {           // at most two passes: unpivoted block LU, then (rarely) the pivoted fallback
             __syncthreads();
-            if (tid == 0) s.flag[2] = 0;
+            if (tid == 0) { s.flag[2] = 0; s.flag[3] = 0; }
             // ---------------- stage 0: proposal (MCMC.py:26) and reduced coordinates ----------------
             if (tid < N2) {
                 double xv = s.xs[tid];
@@ -777,8 +777,7 @@ sweep_kernel(const SweepParams p) {
                     }
                     __syncthreads();
                 }
-                double2 Dr[MB];
-                {
+                auto build_D = [&](double2 (&Dr)[MB]) {
                     const double2 uu = s.us[i], dd = s.dz[i];
                     const double wx = fma(dd.x - mdx, invL, uu.x), wy = fma(dd.y - mdy, invL, uu.y);
 #pragma unroll
@@ -803,11 +802,118 @@ sweep_kernel(const SweepParams p) {
                         }
                         Dr[m] = v;
                     }
+                };
+                // ---- Slater LU, fast path (round 2): the same scheme as the float64 LU below, in FP32 -- entries rounded from the
+                // float64 build, update v += l p as two packed FMAs per entry, one FP32 reciprocal (no Newton steps) -- under the
+                // a-posteriori error indicator es = sum_k k / |u_kk|^2 of the warp kernel (cgb_wsweep.cu; calibration
+                // profiles/r02_slater32_calibration.txt).  Evaluations above the threshold, singular ones and the debug flag
+                // take the float64 LU.
+                bool slater64 = p.force_f64_slater != 0;
+                if (!slater64) {
+                    float2 Df[MB];
+                    {
+                        double2 Dr[MB];
+                        build_D(Dr);
+#pragma unroll
+                        for (int m = 0; m < MB; ++m) Df[m] = make_float2((float)Dr[m].x, (float)Dr[m].y);
+                    }
+                    float2* const fslots = reinterpret_cast<float2*>(s.Rbuf);      // [2][NW][LP]
+                    bool done = !rv, singular = false;
+                    float mypn = 1.f, myerr = 0.f;
+                    unsigned wcand = 0u;
+                    auto offer = [&](int kn) {
+                        const float mag = fabsf(Df[0].x) + fabsf(Df[0].y);
+                        const unsigned key = (done || q != (kn & 3)) ? 0u : ((__float_as_uint(mag) & ~0x3Fu) | (unsigned)row);
+                        wcand = __reduce_max_sync(0xffffffffu, key);
+                        if (lane == 0) s.redD[(kn & 1) * 8 + warp] = wcand;
+                    };
+                    auto publish = [&](int kn) {
+                        if ((wcand >> 6) != 0u && row == (int)(wcand & 0x3Fu)) {
+                            float2* slot = fslots + ((kn & 1) * NW + warp) * LP;
+                            const int nb = kn >> 2;
+#pragma unroll
+                            for (int m = 0; m < MB; ++m) {
+                                if ((m & 3) == 0 && 4 * (nb + m) >= n) break;
+                                slot[4 * (nb + m) + q] = Df[m];
+                            }
+                        }
+                    };
+                    if (tid < 16) s.redD[tid] = 0u;
+                    __syncthreads();
+                    offer(0);
+                    publish(0);
+                    __syncthreads();
+                    for (int base = 0; 4 * base < n; ++base) {
+#pragma unroll
+                        for (int sst = 0; sst < 4; ++sst) {
+                            const int k = 4 * base + sst;
+                            if (k >= n) break;
+                            unsigned gmax;
+                            {
+                                const uint4 ka = *reinterpret_cast<const uint4*>(s.redD + (k & 1) * 8);
+                                const uint4 kb = *reinterpret_cast<const uint4*>(s.redD + (k & 1) * 8 + 4);
+                                gmax = max(max(max(ka.x, ka.y), max(ka.z, ka.w)), max(max(kb.x, kb.y), max(kb.z, kb.w)));
+                            }
+                            singular |= (gmax >> 6) == 0u;
+                            const int pr = (int)(gmax & 0x3Fu);
+                            const float2* cur = fslots + ((k & 1) * NW + (pr >> 3)) * LP;
+                            const float2 piv = cur[k];
+                            const float pn = fmaf(piv.x, piv.x, piv.y * piv.y);
+                            const float ip = rcp_approx(pn);
+                            if (tid == k) { mypn = pn; myerr = (float)(k + 1) * ip; }
+                            if (row == pr) done = true;
+                            if (k == n - 1) break;
+                            if (!__all_sync(0xffffffffu, done)) {
+                                const float ivx = piv.x * ip, ivy = -piv.y * ip;     // 1 / pivot
+                                const float cx = __shfl_sync(0xffffffffu, Df[0].x, qbase + sst);
+                                const float cy = __shfl_sync(0xffffffffu, Df[0].y, qbase + sst);
+                                const float2 L1 = make_float2(-(cx * ivx - cy * ivy), -(cx * ivy + cy * ivx));   // l = -c / pivot
+                                const float2 L2 = make_float2(-L1.y, L1.x);                                      // i l
+#pragma unroll
+                                for (int m = 0; m < MB; ++m) {
+                                    if ((m & 3) == 0 && 4 * (base + m) >= n) break;
+                                    if (m == 4) offer(k + 1);
+                                    const int j = 4 * (base + m) + q;
+                                    if (sst == 3) {
+                                        if (m >= 1) {
+                                            const float2 pv = cur[j];
+                                            Df[m - 1] = __ffma2_rn(make_float2(pv.x, pv.x), L1, __ffma2_rn(make_float2(pv.y, pv.y), L2, Df[m]));
+                                        }
+                                    } else if (m > 0 || q > sst) {
+                                        const float2 pv = cur[j];
+                                        Df[m] = __ffma2_rn(make_float2(pv.x, pv.x), L1, __ffma2_rn(make_float2(pv.y, pv.y), L2, Df[m]));
+                                    }
+                                }
+                                if (4 * (base + 4) >= n || MB <= 4) offer(k + 1);
+                            } else {
+                                offer(k + 1);
+                            }
+                            publish(k + 1);
+                            __syncthreads();
+                        }
+                    }
+                    // log|det| (per-thread pivot moduli, float64 logarithm) and the error indicator, reduced over the CTA
+                    double acc = (tid < n) ? 0.5 * log((double)mypn) : 0.0;
+                    float es = (tid < n) ? myerr : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); es += __shfl_xor_sync(0xffffffffu, es, o); }
+                    if (lane == 0) { s.lsum[warp] = acc; reinterpret_cast<float*>(s.redJ)[warp] = es; }
+                    if (__any_sync(0xffffffffu, singular) && lane == 0) s.flag[3] = 1;
+                    __syncthreads();
+                    float est = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) est += reinterpret_cast<const float*>(s.redJ)[w];
+                    slater64 = !(est < p.slater32_errsum_max * (n > 32 ? 4.f : 1.f)) || s.flag[3] != 0;
+                    __syncthreads();
+                    if (slater64 && tid == 0) { s.flag[3] = 0; if (p.fallback_counter) atomicAdd(p.fallback_counter + 1, 1ull); }
                 }
+                if (slater64) {
                 // ---- Slater LU: partially pivoted, implicit row exchange.  After its update every unfinished row
                 // offers its entry of the next column; one REDUX per warp picks the warp's candidate row, which is
                 // published right away into the warp's own line slot together with its key, so ONE block barrier per
                 // step suffices: after it every thread reads the NW keys, takes the best and reads that warp's slot.
+                double2 Dr[MB];
+                build_D(Dr);
                 double2* const dslots = reinterpret_cast<double2*>(s.Rbuf);       // [2][NW][LP]
                 bool done = !rv, singular = false;
                 double mypn = 1.0;
@@ -895,6 +1001,7 @@ sweep_kernel(const SweepParams p) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (lane == 0) s.lsum[warp] = acc;
+                }   // float64 LU
             }
             __syncthreads();
             if (use_pivot || s.flag[2] == 0) break;
