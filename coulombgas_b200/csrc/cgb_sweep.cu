@@ -808,7 +808,9 @@ sweep_kernel(const SweepParams p) {
                 // a-posteriori error indicator es = sum_k k / |u_kk|^2 of the warp kernel (cgb_wsweep.cu; calibration
                 // profiles/r02_slater32_calibration.txt).  Evaluations above the threshold, singular ones and the debug flag
                 // take the float64 LU.
-                bool slater64 = p.force_f64_slater != 0;
+                // (n <= 16: the float64 LU is cheap and the random-occupation test states there exceed the indicator on every
+                // fourth walker -- measured slower: n=13 B=512 1.43 -> 1.75 ms -- so small n keep the float64 LU)
+                bool slater64 = p.force_f64_slater != 0 || n <= 16;
                 if (!slater64) {
                     float2 Df[MB];
                     {
