@@ -57,6 +57,7 @@ EXPORTS = ("cgb_abi_version", "cgb_error_string", "cgb_ktable_twist_host", "cgb_
 # per-call flags of include/cgb200.h
 KERNELS = {None: 0, "auto": 0, "cta": 1, "cta4": 2, "cta8": 3, "warp": 4, "spec4": 5, "spec8": 6, "spec": 5}
 FLAG_FORCE_PIVOT, FLAG_ADVANCE_KEY, FLAG_FORCE_F64_SLATER = 0x100, 0x200, 0x400
+FLAG_FORCE_SEGMENTS, FLAG_NO_SEGMENTS = 0x800, 0x1000
 STATS_LEN = 8
 
 

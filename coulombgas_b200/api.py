@@ -21,7 +21,8 @@ from ._lib import lib, check, NPARAMS
 # keeps a process-wide default for tests and A/B timings; the environment is read ONCE, here, at import.
 # ----------------------------------------------------------------------------------------------------
 _SWITCH = {"kernel": os.environ.get("CGB_SWEEP_KERNEL") or None, "force_pivot": os.environ.get("CGB_FORCE_PIVOT") == "1",
-           "force_f64_slater": os.environ.get("CGB_FORCE_F64_SLATER") == "1"}
+           "force_f64_slater": os.environ.get("CGB_FORCE_F64_SLATER") == "1",
+           "segments": {"1": True, "0": False}.get(os.environ.get("CGB_SEGMENTS"))}
 if _SWITCH["kernel"] not in _lib.KERNELS:
     raise ValueError("CGB_SWEEP_KERNEL must be one of %s" % sorted(k for k in _lib.KERNELS if k))
 
@@ -35,8 +36,11 @@ def set_sweep_kernel(name=None):
     return prev
 
 
-def set_debug(force_pivot=None, force_f64_slater=None):
-    """Debug paths: the partially pivoted fallback LU of the Jacobian / the float64 Slater LU for every evaluation."""
+def set_debug(force_pivot=None, force_f64_slater=None, segments="keep"):
+    """Debug paths: the partially pivoted fallback LU of the Jacobian / the float64 Slater LU for every evaluation;
+    segments=True cuts every chain of the CTA-per-walker kernel into 2-step segments, False never, None = the launcher's choice."""
+    if segments != "keep":
+        _SWITCH["segments"] = None if segments is None else bool(segments)
     if force_pivot is not None:
         _SWITCH["force_pivot"] = bool(force_pivot)
     if force_f64_slater is not None:
@@ -49,6 +53,8 @@ def _flags(kernel=None):
         f |= _lib.FLAG_FORCE_PIVOT
     if _SWITCH["force_f64_slater"]:
         f |= _lib.FLAG_FORCE_F64_SLATER
+    if _SWITCH["segments"] is not None:
+        f |= _lib.FLAG_FORCE_SEGMENTS if _SWITCH["segments"] else _lib.FLAG_NO_SEGMENTS
     return f
 
 

@@ -134,6 +134,8 @@ static int run_sweep(void* stream, const double* x, double* x_out, const int32_t
     const int sms = wsweep_spec_capacity(n) / 3;
     bool use_warp = wsweep_supported(n) && B > (n <= 16 ? 768 : 384);
     p.cspec = -1;
+    p.seg_len = 0;
+    p.seg_override = (flags & CGB_FLAG_FORCE_SEGMENTS) ? 2 : ((flags & CGB_FLAG_NO_SEGMENTS) ? 0 : -1);
     p.spec = 0;
     if (spec_ok && B > 64) p.spec = B <= sms ? 8 : (B <= 3 * sms ? 4 : 0);
     if (kk == CGB_KERNEL_CTA || kk == CGB_KERNEL_CTA4 || kk == CGB_KERNEL_CTA8) {

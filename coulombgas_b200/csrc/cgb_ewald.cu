@@ -28,7 +28,7 @@ struct EwLay {                      // per-warp shared-memory slice (bytes), n p
         npy = (gmax + 4) & ~3;                 // py harmonics padded to a multiple of 4 (tile width in gy)
         pitch_x = npx + 2;                     // float2 units; +2 keeps 16-byte alignment and spreads rows over the banks
         pitch_y = npy + 2;
-        o_px = 16 * n;                         // double2 u[n] first
+        o_px = 16 * n;                         // float4 u[n] (hi/lo reduced coordinates) first
         o_py = o_px + 8 * n * pitch_x;
         total = (o_py + 8 * n * pitch_y + 15) & ~15;
     }
@@ -38,13 +38,29 @@ __device__ __forceinline__ float2 cmulf(const float2 a, const float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+// erfc(x) for x >= 0: t exp(-x^2 + P(t)), t = 1 / (1 + x/2), P of degree 9 -- the classic Chebyshev-fitted form (fractional error
+// < 1.2e-7 in exact arithmetic; evaluated in FP32: < 1.6e-6 relative for x < 3, 3.7e-7 absolute anywhere; tools/gpu_diag.py and
+// the Ewald parity tests bound the effect on V: < 1e-6 of the energy scale even for random walkers with pairs 0.005 of a cell apart).
+// 15 instructions against ~45 of erfcf, which was 19 % of the kernel.
+__device__ __forceinline__ float erfc_pos(const float x) {
+    const float t = rcp_approx(fmaf(0.5f, x, 1.f));
+    float p = 0.17087277f;
+    p = fmaf(p, t, -0.82215223f); p = fmaf(p, t, 1.48851587f); p = fmaf(p, t, -1.13520398f); p = fmaf(p, t, 0.27886807f);
+    p = fmaf(p, t, -0.18628806f); p = fmaf(p, t, 0.09678418f); p = fmaf(p, t, 0.37409196f); p = fmaf(p, t, 1.00002368f);
+    p = fmaf(p, t, -1.26551223f);
+    return t * ex2_approx((p - x * x) * 1.4426950408889634f);
+}
+
 #ifndef CGBE_WPW2_MAX_BATCH_PER_SM
-#define CGBE_WPW2_MAX_BATCH_PER_SM 8       // two warps per walker while B <= this x #SMs (twice that for n > 32: two particles per lane)
+#define CGBE_WPW2_MAX_BATCH_PER_SM 8       // two warps per walker while B <= this x #SMs (16 for n > 32: two particles per lane)
+#endif
+#ifndef CGBE_MAX_THREADS
+#define CGBE_MAX_THREADS 256
 #endif
 
-__global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
+__global__ void __launch_bounds__(CGBE_MAX_THREADS) ewald_kernel(const EwaldParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_part[8];
+    __shared__ double s_part[8];                 // one per walker of the CTA (at most 8)
     const int n = p.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int wpw = p.wpw;                                   // warps per walker: 1 or 2
     const int grp = wpw == 2 ? warp >> 1 : warp, sub = wpw == 2 ? warp & 1 : 0, ngrp = nwarps / wpw;
@@ -55,24 +71,26 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
     };
     const EwLay L_(n, p.gmax);
     const int tiles_x = L_.npx >> 1, tiles_y = L_.npy >> 2, ntiles = tiles_x * tiles_y;
+    // the first walker's coordinates are requested before the weight table is staged: the two global-memory latencies overlap
+    double2 xpre = make_double2(0.0, 0.0);
+    {
+        const int b = blockIdx.x * ngrp + grp;
+        if (b < p.B && glane < n) xpre = __ldg(reinterpret_cast<const double2*>(p.x) + (size_t)b * n + glane);
+    }
     // dense weights (w+, w-)[gx][gy] over the padded quadrant, CTA-shared
     float2* const Wd = reinterpret_cast<float2*>(smem_raw);
     const int wd_bytes = (8 * L_.npx * L_.npy + 15) & ~15;
+    // the table is zeroed now and filled after the first walker's power tables are built (nothing reads it before the first tile
+    // epilogue): the items' global-memory latency hides behind the table build
+    float4 itpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int)threadIdx.x < p.n_items) itpre = __ldg(p.items + threadIdx.x);
     for (int t = threadIdx.x; t < L_.npx * L_.npy; t += blockDim.x) Wd[t] = make_float2(0.f, 0.f);
-    __syncthreads();
-    for (int t = threadIdx.x; t < p.n_items; t += blockDim.x) {
-        const float4 it = p.items[t];
-        Wd[(int)it.x * L_.npy + (int)it.y] = make_float2(0.5f * it.z, 0.5f * it.w);
-    }
-    __syncthreads();
     unsigned char* const sm = smem_raw + wd_bytes + grp * L_.total;
-    double2* const u = reinterpret_cast<double2*>(sm);
+    float4* const uf = reinterpret_cast<float4*>(sm);        // reduced coordinates split hi / lo: (hi_x, hi_y, lo_x, lo_y)
     float2* const px = reinterpret_cast<float2*>(sm + L_.o_px);
     float2* const py = reinterpret_cast<float2*>(sm + L_.o_py);
     const double invL = 1.0 / p.L;
     const float kap = (float)p.kappa, fn = (float)n;
-    const int npairs = n * (n - 1) / 2;
-    const float tn1 = (float)(2 * n - 1);
 
     for (int b0 = blockIdx.x * ngrp; b0 < p.B; b0 += gridDim.x * ngrp) {      // the same trip count for every warp of the CTA
         const int b = b0 + grp;
@@ -80,54 +98,73 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
         group_sync();
         // ---- reduced coordinates and power tables e^{2 pi i g u}, g = 0..gmax (padding harmonics = 0)
         for (int i = glane; live && i < n; i += gsize) {
-            double2 xv = __ldg(reinterpret_cast<const double2*>(p.x) + (size_t)b * n + i);
+            double2 xv = (b0 == blockIdx.x * ngrp && i == glane) ? xpre
+                                                                 : __ldg(reinterpret_cast<const double2*>(p.x) + (size_t)b * n + i);
             xv.x *= invL; xv.y *= invL;                                   // x / L  (potential.py:77)
             xv.x -= floor(xv.x); xv.y -= floor(xv.y);
-            u[i] = xv;
-#pragma unroll 1
+            const float uhx = (float)xv.x, uhy = (float)xv.y;
+            const float ulx = (float)(xv.x - (double)uhx), uly = (float)(xv.y - (double)uhy);
+            uf[i] = make_float4(uhx, uhy, ulx, uly);
+            // both coordinates at once, even and odd harmonics as two independent chains (each multiplies by p1^2): four
+            // independent complex products per step instead of a serial chain of 2 (gmax + 1) per coordinate
+            float2 p1[2], p2[2], ev[2], od[2];
+#pragma unroll
             for (int comp = 0; comp < 2; ++comp) {
-                const double uc = comp ? xv.y : xv.x;
-                const float uh = (float)uc, ul = (float)(uc - (double)uh);
+                const float uh = comp ? uhy : uhx, ul = comp ? uly : ulx;
                 float sn, cs;
                 sincospif(2.f * uh, &sn, &cs);
                 const float pl = 2.f * kPi * ul;                          // first-order hi/lo correction of the phase
-                const float2 p1 = make_float2(fmaf(-pl, sn, cs), fmaf(pl, cs, sn));
-                float2* row = comp ? (py + i * L_.pitch_y) : (px + i * L_.pitch_x);
-                const int np = comp ? L_.npy : L_.npx;
-                float2 pw = make_float2(1.f, 0.f);
-                for (int g = 0; g < np; g += 2) {
-                    const float2 a = g <= p.gmax ? pw : make_float2(0.f, 0.f);
-                    pw = cmulf(pw, p1);
-                    const float2 c = g + 1 <= p.gmax ? pw : make_float2(0.f, 0.f);
-                    pw = cmulf(pw, p1);
-                    *reinterpret_cast<float4*>(row + g) = make_float4(a.x, a.y, c.x, c.y);
-                }
+                p1[comp] = make_float2(fmaf(-pl, sn, cs), fmaf(pl, cs, sn));
+                p2[comp] = cmulf(p1[comp], p1[comp]);
+                ev[comp] = make_float2(1.f, 0.f);
+                od[comp] = p1[comp];
+            }
+            float2* const rowx = px + i * L_.pitch_x;
+            float2* const rowy = py + i * L_.pitch_y;
+            for (int g = 0; g < L_.npy; g += 2) {                          // npy >= npx
+                const bool in0 = g <= p.gmax, in1 = g + 1 <= p.gmax;
+                if (g < L_.npx)
+                    *reinterpret_cast<float4*>(rowx + g) = make_float4(in0 ? ev[0].x : 0.f, in0 ? ev[0].y : 0.f, in1 ? od[0].x : 0.f, in1 ? od[0].y : 0.f);
+                *reinterpret_cast<float4*>(rowy + g) = make_float4(in0 ? ev[1].x : 0.f, in0 ? ev[1].y : 0.f, in1 ? od[1].x : 0.f, in1 ? od[1].y : 0.f);
+                ev[0] = cmulf(ev[0], p2[0]); od[0] = cmulf(od[0], p2[0]);
+                ev[1] = cmulf(ev[1], p2[1]); od[1] = cmulf(od[1], p2[1]);
             }
         }
-        group_sync();
-        float acc = 0.f;
+        if (b0 == blockIdx.x * ngrp) {                   // first walker of the CTA: stage the weights (CTA-uniform branch)
+            __syncthreads();
+            if ((int)threadIdx.x < p.n_items) Wd[(int)itpre.x * L_.npy + (int)itpre.y] = make_float2(0.5f * itpre.z, 0.5f * itpre.w);
+            for (int t = threadIdx.x + blockDim.x; t < p.n_items; t += blockDim.x) {
+                const float4 it = __ldg(p.items + t);
+                Wd[(int)it.x * L_.npy + (int)it.y] = make_float2(0.5f * it.z, 0.5f * it.w);
+            }
+            __syncthreads();
+        } else group_sync();
+        float acc = 0.f, accr = 0.f;          // two accumulators added in a fixed order: the result does not depend on the warp
         // ---- reciprocal space: 2 x 4 register tile of (gx, gy) per lane
+        auto reciprocal_space = [&]() {
         for (int tile = glane; live && tile < ntiles; tile += gsize) {
             const int tx = tile / tiles_y, ty = tile - tx * tiles_y;
             const float4* pxa = reinterpret_cast<const float4*>(px + 2 * tx);
             const float4* pya = reinterpret_cast<const float4*>(py + 4 * ty);
-            float ac[2][4], bd[2][4], ad[2][4], bc[2][4];
+            // (ac, ad) += xr (yr, yi) and (bc, bd) += xi (yr, yi): the (re, im) pairs of py are register pairs as loaded, so every
+            // particle costs 16 packed FMAs (FFMA2, scalar operand broadcast) instead of 32 scalar ones
+            float2 A[2][4], Bq[2][4];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { ac[a][c] = 0.f; bd[a][c] = 0.f; ad[a][c] = 0.f; bc[a][c] = 0.f; }
+                for (int c = 0; c < 4; ++c) { A[a][c] = make_float2(0.f, 0.f); Bq[a][c] = make_float2(0.f, 0.f); }
 #pragma unroll 2
             for (int i = 0; i < n; ++i) {
                 const float4 xa = pxa[i * (L_.pitch_x >> 1)];
                 const float4 y0 = pya[i * (L_.pitch_y >> 1)], y1 = pya[i * (L_.pitch_y >> 1) + 1];
                 const float xr[2] = {xa.x, xa.z}, xi[2] = {xa.y, xa.w};
-                const float yr[4] = {y0.x, y0.z, y1.x, y1.z}, yi[4] = {y0.y, y0.w, y1.y, y1.w};
+                const float2 Y[4] = {make_float2(y0.x, y0.y), make_float2(y0.z, y0.w), make_float2(y1.x, y1.y), make_float2(y1.z, y1.w)};
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        ac[a][c] = fmaf(xr[a], yr[c], ac[a][c]); bd[a][c] = fmaf(xi[a], yi[c], bd[a][c]);
-                        ad[a][c] = fmaf(xr[a], yi[c], ad[a][c]); bc[a][c] = fmaf(xi[a], yr[c], bc[a][c]);
+                        A[a][c] = __ffma2_rn(make_float2(xr[a], xr[a]), Y[c], A[a][c]);
+                        Bq[a][c] = __ffma2_rn(make_float2(xi[a], xi[a]), Y[c], Bq[a][c]);
                     }
             }
 #pragma unroll
@@ -135,30 +172,43 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float2 w = Wd[(2 * tx + a) * L_.npy + 4 * ty + c];
-                    const float spr = ac[a][c] - bd[a][c], spi = ad[a][c] + bc[a][c];
-                    const float smr = ac[a][c] + bd[a][c], smi = bc[a][c] - ad[a][c];
+                    const float spr = A[a][c].x - Bq[a][c].y, spi = A[a][c].y + Bq[a][c].x;      // S+ = sum px py
+                    const float smr = A[a][c].x + Bq[a][c].y, smi = Bq[a][c].x - A[a][c].y;      // S- = sum px conj(py)
                     acc = fmaf(w.x, fmaf(spr, spr, spi * spi) - fn, acc);
                     acc = fmaf(w.y, fmaf(smr, smr, smi * smi) - fn, acc);
                 }
         }
-        // ---- real space, nearest image (potential.py:45-50): pair index q -> (i < j), row i starts at i(2n-1-i)/2
-        for (int q = glane; live && q < npairs; q += gsize) {
-            int i = (int)((tn1 - sqrtf(fmaf(tn1, tn1, -8.f * (float)q))) * 0.5f);
-            i = max(0, min(i, n - 2));
-            int r0 = (i * (2 * n - 1 - i)) >> 1;
-            if (r0 > q) { --i; r0 = (i * (2 * n - 1 - i)) >> 1; }
-            else if (q - r0 >= n - 1 - i) { r0 += n - 1 - i; ++i; }
-            const int j = i + 1 + (q - r0);
-            const double2 ui = u[i], uj = u[j];
-            double dx = ui.x - uj.x, dy = ui.y - uj.y;
-            dx -= rint(dx);
-            dy -= rint(dy);
-            const float fx = (float)dx, fy = (float)dy;
-            const float d2 = fmaf(fx, fx, fy * fy);
-            const float rd = rsqrtf(d2);
-            acc = fmaf(erfcf(kap * (d2 * rd)), rd, acc);
-        }
-        double a = (double)acc;
+        };
+        // ---- real space, nearest image (potential.py:45-50).  The n(n-1)/2 pairs are enumerated as a circulant: particle i
+        // meets i+d (mod n), d = 1..n/2 (for even n the last offset only from the lower half) -- no index decode, the own
+        // coordinates stay in registers, the partners of a warp are consecutive shared-memory words.  Differences from the
+        // hi/lo split (error < 1e-8 of a cell), nearest image by the round-to-nearest magic constant.
+        auto real_space = [&]() {
+            const int half = n >> 1;
+            const bool wide = n > 32;                     // two particles per lane (one per thread when the walker has two warps)
+            const int d0 = wide ? 1 : 1 + sub, dstep = wide ? 1 : wpw;
+            for (int i = wide ? glane : lane; live && i < n; i += wide ? gsize : 32) {
+                const float4 ui = uf[i];
+                const int dmax = (2 * half == n && i >= half) ? half - 1 : half;
+#pragma unroll 2
+                for (int d = d0; d <= dmax; d += dstep) {
+                    int j = i + d;
+                    j = j >= n ? j - n : j;
+                    const float4 uj = uf[j];
+                    float fx = (ui.x - uj.x) + (ui.z - uj.z), fy = (ui.y - uj.y) + (ui.w - uj.w);
+                    fx -= (fx + 12582912.f) - 12582912.f;                      // rint for |f| < 2^22
+                    fy -= (fy + 12582912.f) - 12582912.f;
+                    const float d2 = fmaf(fx, fx, fy * fy);
+                    const float rd = rsqrt_approx(d2);                         // d2 >= 1e-12 for distinct particles: no denormals
+                    accr = fmaf(erfc_pos(kap * (d2 * rd)), rd, accr);
+                }
+            }
+        };
+        // the tile loop is bound by the FMA pipe, the pair loop by its dependency chain (rsqrt -> rcp -> Horner -> ex2): half of the
+        // warps of every scheduler (warp = 4 k + scheduler) take them in the other order, so the two phases overlap on the SM
+        if ((warp >> 2) & 1) { real_space(); reciprocal_space(); }
+        else { reciprocal_space(); real_space(); }
+        double a = (double)(acc + accr);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (wpw == 2) {                                   // the second warp hands its partial sum to the first (fixed order)
@@ -176,7 +226,7 @@ __global__ void __launch_bounds__(256) ewald_kernel(const EwaldParams p) {
     // reduces out[0..B) in a fixed order -> deterministic sums, no second kernel, no floating-point atomics
     if (p.stats) {
         __shared__ bool s_last;
-        __shared__ double s_red[2][8];
+        __shared__ double s_red[2][CGBE_MAX_THREADS / 32];
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -210,14 +260,20 @@ int launch_ewald(const EwaldParams& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // two warps per walker while one warp per walker cannot fill the machine (see the header of this file)
     EwaldParams q = p;
-    // measured (profiles/r02_time_ewald.txt): n=29: B=256 6.2 vs 8.2 us, B=2048 14.2 vs 11.7 us (the second half-wave costs more
-    // than the shorter chains save); n=57: B=512 12.5 vs 18.3 us, B=2048 29.8 vs 39.3 us
-    q.wpw = (long long)p.B <= (long long)CGBE_WPW2_MAX_BATCH_PER_SM * (p.n > 32 ? 2 : 1) * sms ? 2 : 1;
+    // measured (profiles/r02_time_ewald.txt): n=29: B=256 5.1 vs 6.9 us, B=2048 11.9 vs 8.3 us (28 warps per SM in two 448-thread CTAs at
+    // 72 registers: the half-warps' shorter chains do not pay for the second barrier-coupled warp); n=57: B=512 8.3 vs 12.5 us
+    q.wpw = (long long)p.B <= (long long)(p.n > 32 ? 16 : CGBE_WPW2_MAX_BATCH_PER_SM) * sms ? 2 : 1;
     // walkers per CTA: 8 (4 with two warps each) while three CTAs still fit one SM's shared memory, fewer for large n / gmax;
     // small batches use smaller CTAs so that the walkers spread over all SMs
-    int gpc = 8 / q.wpw;
-    while (gpc > 1 && (size_t)wd_bytes + (size_t)gpc * L_.total > 72 * 1024) gpc >>= 1;
-    while (gpc > 1 && (long long)p.B < (long long)sms * gpc) gpc >>= 1;
+    int gpc = q.wpw == 2 ? CGBE_MAX_THREADS / 64 : 8;
+    while (gpc > 1 && (size_t)wd_bytes + (size_t)gpc * L_.total > 72 * 1024) --gpc;
+    if ((long long)p.B < (long long)sms * gpc) gpc = p.B / sms > 1 ? p.B / sms : 1;
+    // a batch of a few waves: even out the warps per SM (2048 walkers on 148 SMs are 13.8 per SM: two CTAs of 7 on every SM
+    // instead of two CTAs of 8 on 108 SMs and one on 40)
+    if ((long long)p.B >= (long long)sms * gpc && (long long)p.B <= 3ll * sms * gpc) {
+        const int per_sm = (int)(((long long)p.B + sms - 1) / sms), ctas = (per_sm + gpc - 1) / gpc;
+        gpc = (per_sm + ctas - 1) / ctas;
+    }
     const int wpc = gpc * q.wpw;
     const size_t smem = (size_t)wd_bytes + (size_t)gpc * L_.total;
     if (smem > 227 * 1024) return CGB_E_UNSUPPORTED;

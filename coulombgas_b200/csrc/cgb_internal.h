@@ -59,6 +59,8 @@ struct SweepParams {
     int* done;                    // (B) steps completed per walker
     double* ws_logp;              // (B) current log p per walker
     int* ws_nacc;                 // (B) accepted moves so far
+    int seg_len;                  // CTA kernel: steps per chain segment (0 = whole chains, static assignment); set by the launcher
+    int seg_override;             // -1 = launcher's choice, else forced segment length (tests)
     int cspec;                    // CTA kernel's speculative mode: -1 = auto (widest tree that fits), 0 = off, 4/8 = CTAs per walker
     unsigned long long* prof;     // developer builds (CGBW_PROF): 12 per-phase cycle sums in the workspace, else unused
     unsigned n_sms;               // multiprocessors of the device (CTA i starts on SM i % n_sms)

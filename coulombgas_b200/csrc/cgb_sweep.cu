@@ -24,8 +24,10 @@ namespace cgb {
 // parameter packing: float64 haiku-order vector -> FP32 kernel layout (Wt, bt pre-scaled by log2 e)
 // ---------------------------------------------------------------------------------------------------
 __global__ void prep_params_kernel(const double* __restrict__ p, float* __restrict__ w, double* stats, double nprop,
-                                   uint32_t* key_dev, int advance_key) {
-    if (threadIdx.x == 0) {       // prologue duties of the sampling step (include/cgb200.h: CGB_STATS_*, CGB_FLAG_ADVANCE_KEY)
+                                   uint32_t* key_dev, int advance_key, int* seg_done, unsigned long long* ticket, int B) {
+    for (int t = threadIdx.x; t < B; t += blockDim.x) seg_done[t] = 0;        // segmented sweeps (sweep_kernel, seg_len > 0)
+    if (threadIdx.x == 0) {
+        *ticket = 0ull;       // prologue duties of the sampling step (include/cgb200.h: CGB_STATS_*, CGB_FLAG_ADVANCE_KEY)
         if (stats) { for (int t = 0; t < CGB_STATS_LEN; ++t) stats[t] = 0.0; stats[CGB_STATS_NPROPOSED] = nprop; }
         if (key_dev && advance_key) {
             const uint64_t k = (((uint64_t)key_dev[0] << 32) | (uint64_t)key_dev[1]) + 0x9E3779B97F4A7C15ull;
@@ -141,6 +143,15 @@ __device__ __forceinline__ double quad_sum_f64(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
 }
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Kahan-compensated accumulation: the sums over partners feed the Slater phases, whose condition number
 // amplifies FP32 summation error past the 1e-5 budget.
 __device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
@@ -249,10 +260,37 @@ sweep_kernel(const SweepParams p) {
     double* const splp = reinterpret_cast<double*>(smem_raw + L_::o_red + 144);     // [2] this CTA's node log p, double-buffered
     int sp_round = 0;
 
-    for (int b = blockIdx.x / CW; b < p.B; b += gridDim.x / CW) {
+    // Work items.  Default: one item per walker (its whole chain), dealt statically.  Segmented mode (seg_len > 0; batches of a
+    // few walkers per resident CTA, where whole chains leave a ragged last wave -- 512 walkers on 296 CTA slots are two rounds
+    // for 1.73 rounds of work): a chain is cut into segments of seg_len steps, item = (segment, walker) in segment-major order,
+    // taken by a global ticket; a segment waits for its walker's previous one (done[b], release / acquire), which was ticketed
+    // earlier and therefore belongs to a running CTA -- no deadlock whatever else occupies the device.  State between the
+    // segments of a walker travels through x_out / ws_logp / ws_nacc.
+    const bool segmented = SPECC == 0 && p.seg_len > 0;
+    const int nseg = segmented ? (p.mc_steps + p.seg_len - 1) / p.seg_len : 1;
+    const int nitems = nseg * p.B;                       // the launcher keeps this below 2^31
+    __shared__ int s_item;
+    int item = (int)(blockIdx.x / CW) - (int)(gridDim.x / CW);
+    for (;;) {
+        if (segmented) {
+            __syncthreads();
+            if (tid == 0) s_item = (int)atomicAdd(p.qctr, 1ull);
+            __syncthreads();
+            item = s_item;
+        } else {
+            item += gridDim.x / CW;
+        }
+        if (item >= nitems) break;
+        const int seg = segmented ? item / p.B : 0, b = item - seg * p.B;
+        const int step_lo = seg == 0 ? 0 : seg * p.seg_len + 1;
+        const int step_hi = segmented ? min((seg + 1) * p.seg_len, p.mc_steps) : p.mc_steps;
+        const bool last_seg = seg == nseg - 1;
+        if (seg > 0 && tid == 0) {
+            while (ld_acquire_s32(p.done + b) < seg) __nanosleep(200);
+        }
         __syncthreads();
         if (tid == 0) s.flag[1] = 0;
-        if (tid < N2) s.xs[tid] = p.x[(size_t)b * N2 + tid];
+        if (tid < N2) s.xs[tid] = seg == 0 ? p.x[(size_t)b * N2 + tid] : __ldcg(p.x_out + (size_t)b * N2 + tid);
         __syncthreads();
         if (tid < n) {
             int si = p.state_idx[(size_t)b * n + tid];
@@ -264,12 +302,13 @@ sweep_kernel(const SweepParams p) {
         double logp_cur = 0.0;   // thread 0 only
         int nacc = 0;            // thread 0 only (speculative mode: every thread)
         int t_done = 0;          // speculative mode: steps decided so far
+        if (seg > 0 && tid == 0) { logp_cur = __ldcg(p.ws_logp + b); nacc = __ldcg(p.ws_nacc + b); }
 
-        for (int it = 0;; ++it) {
+        for (int it = step_lo;; ++it) {
           int step = it, node = 0, depth = 0;
           bool active = true;
           if constexpr (SPECC == 0) {
-              if (step > p.mc_steps) break;
+              if (step > step_hi) break;
           } else {
               if (it > 0 && t_done >= p.mc_steps) break;
               node = crank + 1;                              // heap numbering: child of m is 2m + accepted
@@ -1095,13 +1134,22 @@ sweep_kernel(const SweepParams p) {
         __syncthreads();
         if (p.mc_steps > 0 && tid < N2 && crank == 0) {
             double xv = s.xs[tid];
-            if (p.wrap) xv -= p.L * floor(xv / p.L);             // VMC.py:24
+            if (p.wrap && last_seg) xv -= p.L * floor(xv / p.L);             // VMC.py:24
             p.x_out[(size_t)b * N2 + tid] = xv;
         }
         if (tid == 0 && crank == 0) {
-            if (p.out_logp) p.out_logp[b] = logp_cur;
-            if (p.out_naccept) p.out_naccept[b] = nacc;
-            if (p.out_stats && p.mc_steps > 0) atomicAdd(p.out_stats + CGB_STATS_NACCEPT, (double)nacc);   // integers: exact, order-free
+            if (last_seg) {
+                if (p.out_logp) p.out_logp[b] = logp_cur;
+                if (p.out_naccept) p.out_naccept[b] = nacc;
+                if (p.out_stats && p.mc_steps > 0) atomicAdd(p.out_stats + CGB_STATS_NACCEPT, (double)nacc);   // integers: exact, order-free
+            } else {
+                p.ws_logp[b] = logp_cur; p.ws_nacc[b] = nacc;
+            }
+        }
+        if (!last_seg) {                                  // hand the walker to whoever holds its next segment
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) { __threadfence(); st_release_s32(p.done + b, seg + 1); }
         }
     }
     if constexpr (SPECC != 0) cluster_sync_all();     // no CTA leaves while a neighbour may still read its log p slots
@@ -1150,7 +1198,17 @@ static int launch_nw(const SweepParams& p, cudaStream_t st) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<NW, 0>, NW * 32, smem);
     if (occ < 1) occ = 1;
     int grid = p.B < sms * occ ? p.B : sms * occ;
-    sweep_kernel<NW, 0><<<grid, NW * 32, smem, st>>>(p);
+    SweepParams q = p;
+    q.seg_len = 0;
+    if (NW >= 5 && p.mc_steps >= 8 && p.B > grid) {
+        // whole chains: ceil(B / grid) rounds; segments of mc_steps / 16 steps level that to within a few per cent.  Only where an
+        // evaluation is long against a segment's start-up (n > 32) and the ragged wave costs more than 3 %
+        const long long rounds = ((long long)p.B + grid - 1) / grid;
+        if ((double)(rounds * grid) > 1.03 * (double)p.B) q.seg_len = p.mc_steps / 16 > 1 ? p.mc_steps / 16 : 1;
+    }
+    if (p.seg_override >= 0) q.seg_len = p.seg_override < p.mc_steps ? p.seg_override : 0;
+    if (q.seg_len > 0 && ((long long)p.mc_steps / q.seg_len + 2) * (long long)p.B + (long long)grid >= (1ll << 31)) q.seg_len = 0;
+    sweep_kernel<NW, 0><<<grid, NW * 32, smem, st>>>(q);
     return (int)cudaGetLastError();
 }
 
@@ -1169,7 +1227,7 @@ int launch_sweep(const SweepParams& p, cudaStream_t st) {
 
 int launch_prep_params(const SweepParams& p, float* wpack, cudaStream_t st) {
     prep_params_kernel<<<1, 256, 0, st>>>(p.params, wpack, p.out_stats, (double)p.B * (double)p.mc_steps,
-                                          const_cast<uint32_t*>(p.key_dev), p.advance_key);
+                                          const_cast<uint32_t*>(p.key_dev), p.advance_key, p.done, p.qctr, p.B);
     return (int)cudaGetLastError();
 }
 

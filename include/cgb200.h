@@ -67,6 +67,9 @@ extern "C" {
 #define CGB_FLAG_FORCE_PIVOT  0x100u   /* debug: Jacobian log-det by the partially pivoted fallback LU */
 #define CGB_FLAG_ADVANCE_KEY  0x200u   /* sweep: key_dev <- key_dev + golden-ratio increment BEFORE it is used (see below) */
 #define CGB_FLAG_FORCE_F64_SLATER 0x400u   /* debug: Slater log-det by the float64 LU even where the FP32 LU passes its monitor */
+#define CGB_FLAG_FORCE_SEGMENTS  0x800u   /* debug: CTA-per-walker kernel cuts every chain into 2-step segments handed from CTA to CTA
+                                            * (the load-balancing mode it picks itself for n > 32 and a few walkers per CTA slot) */
+#define CGB_FLAG_NO_SEGMENTS    0x1000u   /* A/B timing: never cut chains into segments */
 
 /* Statistics vector of one sampling step (device, CGB_STATS_LEN float64): what the reference's pmean sites reduce
  * (src/MCMC.py:38-39 accept rate; the V_mean / V2_mean entries of src/VMC.py:46-53).  One all-reduce (sum) of entries 0..4

@@ -423,6 +423,44 @@ def test_cluster_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeyp
             assert acca == accb
 
 
+@pytest.mark.parametrize("tag,B,S", [("n57_rs0.25", 5, 7), ("n57_rs0.25", 350, 9), ("n49_rs0.5", 33, 5), ("n13_rs10", 70, 11),
+                                     ("n29_rs1", 9, 2), ("n29_rs1", 40, 3)])
+def test_segmented_chains_are_bit_identical(cg, cases, tag, B, S):
+    """CTA-per-walker kernel, segmented mode (load balancing for a few walkers per resident CTA): every chain is
+    cut into segments that different CTAs take by ticket, the walker's state (x, log p, accepted count) travels through global
+    memory.  Must be the very same computation: accept masks, log p traces, final walkers (wrapped once, at the end),
+    counts and the statistics vector bit-identical to whole chains -- in parity mode and with the in-kernel Philox streams.
+    B = 350 at n = 57 exceeds the 296 resident CTAs, so tickets are really taken by whoever is free."""
+    c = cases(tag)
+    reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+    rng = np.random.default_rng(5)
+    x0 = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2)) + 2.0 * c["L"]   # off-cell: the wrap matters
+    si = np.tile(c["state_idx"], (reps, 1))[:B]
+    logp = cg.make_logp(c["ktable"], c["L"])
+    noise, unif = rng.standard_normal((S, B, c["n"], 2)), rng.uniform(size=(S, B))
+    prev = cg.set_sweep_kernel("cta")
+    out = {}
+    try:
+        for seg in (False, True):
+            cg.set_debug(segments=seg)
+            st = torch.zeros(8, dtype=torch.float64, device="cuda")
+            out[seg, "philox"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, wrap_L=c["L"], return_trace=True, stats=st)
+            out[seg, "stats"] = st.cpu().numpy()
+            out[seg, "explicit"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), cg.ExplicitNoise(noise, unif), S, 0.1,
+                                           wrap_L=c["L"], return_trace=True)
+    finally:
+        cg.set_debug(segments=None)
+        cg.set_sweep_kernel(prev)
+    for k in ("philox", "explicit"):
+        (xa, acca, tra), (xb, accb, trb) = out[False, k], out[True, k]
+        for f in ("accept", "logp_prop", "logp", "naccept"):
+            assert np.array_equal(tra[f], trb[f]), (k, f)
+        assert np.array_equal(xa, xb), k
+        assert acca == accb
+        assert xb.min() >= 0.0 and xb.max() < c["L"]
+    assert np.array_equal(out[False, "stats"], out[True, "stats"])
+
+
 @pytest.mark.parametrize("n", [9, 21, 25])
 def test_other_warp_kernel_instances(cg, oracle, n, monkeypatch):
     """The warp-per-walker kernel is also instantiated for the other 2D closed shells below one warp (n = 9, 21, 25):
