@@ -14,6 +14,10 @@ for tag, B in (("n13_rs10", 3), ("n29_rs1", 3), ("n49_rs0.5", 2), ("n57_rs0.25",
         cg.set_sweep_kernel(kern)
         lp = logp(x, c["params"], si)
         xs, acc = cg.mcmc(logp.bind(c["params"], si), x.copy(), 5, 4, 0.1)
+    cg.set_sweep_kernel("cta")
+    cg.set_debug(segments=True)                                    # chains cut into ticketed segments (flag hand-over through global memory)
+    xs, acc = cg.mcmc(logp.bind(c["params"], si), x.copy(), 5, 5, 0.1, wrap_L=c["L"])
+    cg.set_debug(segments=None)
     cg.set_sweep_kernel(None)
     cg.set_debug(force_pivot=True)
     lp2 = logp(x, c["params"], si)
