@@ -6,16 +6,20 @@
 // quadruple sharing one set of four real accumulators (host-side merge in cgb_ewald_prepare_host).
 // Real space: nearest image only, erfc(kappa d)/d (potential.py:45-50).
 //
-// One WARP per walker (persistent over the batch), no block barrier after the weight table is staged:
+// One WARP per walker (persistent over the batch), no block barrier once the weight table is staged:
 //   * lane i builds the power tables of particles i, i+32: ONE sincospi per coordinate (phase reduced in float64,
-//     hi/lo corrected), higher harmonics by complex multiplication;
+//     hi/lo corrected), higher harmonics by complex multiplication -- both coordinates and the even / odd harmonics as four
+//     independent chains;
 //   * the reciprocal sum is a small complex matrix product  S+-(gx,gy) = sum_i px_i[gx] py_i[gy]^(*)  over the
-//     (gmax+1)^2 quadrant, register-tiled 2 x 4 per lane: per particle 3 broadcast LDS.128 feed 32 FFMA; the
-//     merged weights (w+, w-) sit in a dense CTA-shared table (zero outside the |G| <= Gmax disc);
-//   * the n(n-1)/2 real-space pairs are dealt round-robin to the lanes (triangular index decoded per pair);
-//   * batches that cannot fill the GPU with one warp per walker (the named 2048-walker batch: 0.58 waves) give every walker
-//     TWO warps: the pair shares the walker's tables, splits the particles of the table build, the tiles and the pairs, and
-//     meets at a named barrier (64 threads) -- per-walker latency halves, 4096 warps fill the 148 SMs in one wave.
+//     (gmax+1)^2 quadrant, register-tiled 2 x 4 per lane: per particle 3 broadcast LDS.128 feed 16 packed FMAs (FFMA2:
+//     (ac, ad) += xr (yr, yi), (bc, bd) += xi (yr, yi)); the merged weights (w+, w-) sit in a dense CTA-shared table (zero
+//     outside the |G| <= Gmax disc);
+//   * the n(n-1)/2 real-space pairs are enumerated as a circulant (particle i meets i+d mod n, d = 1..n/2): no index decode,
+//     differences from a hi/lo float split of the reduced coordinates, a 15-instruction erfc (erfc_pos below);
+//   * half of every scheduler's warps run the two loops in the other order (one is FMA-pipe-bound, the other latency-bound);
+//   * batches that cannot fill the GPU with one warp per walker give every walker TWO warps: the pair shares the walker's
+//     tables, splits the particles of the table build, the tiles and the pairs, and meets at a named barrier (64 threads);
+//   * a batch of one to three waves gets CTAs of equal size on every SM (launch_ewald).
 #include "cgb_common.cuh"
 #include "cgb_internal.h"
 
