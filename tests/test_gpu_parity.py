@@ -73,6 +73,24 @@ def test_ewald_random_and_edge_cases(cg, oracle):
     assert np.abs(V2 - ref).max() < RTOL * np.abs(ref).max()
 
 
+def test_ewald_one_and_two_warps_per_walker_agree(cg, cases, oracle):
+    """The Ewald launcher gives a walker two warps while the batch is below one wave (B <= 8 x #SMs, 16 x for n > 32) and one
+    warp above; n > 32 puts two particles on a lane.  All four combinations against each other (the same walkers in one big
+    and several small calls; they sum in different orders: 1e-6 of the energy scale) and against the oracle on a subsample."""
+    rng = np.random.default_rng(3)
+    for tag, B in (("n57_rs0.25", 2600), ("n29_rs1", 1500), ("n13_rs10", 1300)):
+        c = cases(tag)
+        reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+        x = np.tile(c["x"], (reps, 1, 1))[:B] + 0.05 * rng.standard_normal((B, c["n"], 2))
+        Vbig = cg.potential_energy(x, c["kappa"], c["G"], c["L"], c["rs"])
+        Vsmall = np.concatenate([cg.potential_energy(x[a:a + 300], c["kappa"], c["G"], c["L"], c["rs"]) for a in range(0, B, 300)])
+        scale = np.abs(Vbig).max()
+        assert np.abs(Vbig - Vsmall).max() < 1e-6 * scale, tag
+        sub = rng.choice(B, 12, replace=False)
+        ref = oracle["potential"].potential_energy(x[sub], c["kappa"], c["G"], c["L"], c["rs"])
+        assert np.abs(Vbig[sub] - ref).max() < RTOL * scale, tag
+
+
 # ------------------------------------------------------------------ log p
 @pytest.mark.parametrize("tag", CASES_2D)
 def test_logp_golden(cg, cases, tag):
