@@ -441,14 +441,17 @@ def test_cluster_speculative_mode_is_bit_identical(cg, cases, tag, B, S, monkeyp
             assert acca == accb
 
 
-@pytest.mark.parametrize("tag,B,S", [("n57_rs0.25", 5, 7), ("n57_rs0.25", 350, 9), ("n49_rs0.5", 33, 5), ("n13_rs10", 70, 11),
-                                     ("n29_rs1", 9, 2), ("n29_rs1", 40, 3)])
-def test_segmented_chains_are_bit_identical(cg, cases, tag, B, S):
+@pytest.mark.parametrize("tag,B,S,mode", [("n57_rs0.25", 5, 7, True), ("n57_rs0.25", 350, 9, True), ("n49_rs0.5", 33, 5, True),
+                                          ("n13_rs10", 70, 11, True), ("n29_rs1", 9, 2, True), ("n29_rs1", 40, 3, True),
+                                          ("n57_rs0.25", 340, 16, None), ("n49_rs0.5", 512, 32, None)])
+def test_segmented_chains_are_bit_identical(cg, cases, tag, B, S, mode):
     """CTA-per-walker kernel, segmented mode (load balancing for a few walkers per resident CTA): every chain is
     cut into segments that different CTAs take by ticket, the walker's state (x, log p, accepted count) travels through global
     memory.  Must be the very same computation: accept masks, log p traces, final walkers (wrapped once, at the end),
     counts and the statistics vector bit-identical to whole chains -- in parity mode and with the in-kernel Philox streams.
-    B = 350 at n = 57 exceeds the 296 resident CTAs, so tickets are really taken by whoever is free."""
+    B = 350 at n = 57 exceeds the 296 resident CTAs, so tickets are really taken by whoever is free.  mode = True forces 2-step
+    segments (CGB_FLAG_FORCE_SEGMENTS), mode = None is the launcher's own choice (it segments these two shapes: more walkers than
+    CTA slots, ragged last round) -- both against whole chains (CGB_FLAG_NO_SEGMENTS)."""
     c = cases(tag)
     reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
     rng = np.random.default_rng(5)
@@ -459,7 +462,7 @@ def test_segmented_chains_are_bit_identical(cg, cases, tag, B, S):
     prev = cg.set_sweep_kernel("cta")
     out = {}
     try:
-        for seg in (False, True):
+        for seg in (False, mode):
             cg.set_debug(segments=seg)
             st = torch.zeros(8, dtype=torch.float64, device="cuda")
             out[seg, "philox"] = cg.mcmc(logp.bind(c["params"], si), x0.copy(), 99, S, 0.1, wrap_L=c["L"], return_trace=True, stats=st)
@@ -470,13 +473,13 @@ def test_segmented_chains_are_bit_identical(cg, cases, tag, B, S):
         cg.set_debug(segments=None)
         cg.set_sweep_kernel(prev)
     for k in ("philox", "explicit"):
-        (xa, acca, tra), (xb, accb, trb) = out[False, k], out[True, k]
+        (xa, acca, tra), (xb, accb, trb) = out[False, k], out[mode, k]
         for f in ("accept", "logp_prop", "logp", "naccept"):
             assert np.array_equal(tra[f], trb[f]), (k, f)
         assert np.array_equal(xa, xb), k
         assert acca == accb
         assert xb.min() >= 0.0 and xb.max() < c["L"]
-    assert np.array_equal(out[False, "stats"], out[True, "stats"])
+    assert np.array_equal(out[False, "stats"], out[mode, "stats"])
 
 
 @pytest.mark.parametrize("n", [9, 21, 25])
