@@ -136,6 +136,43 @@ def test_two_streams_two_parameter_sets(cg, cases):
         cg.set_sweep_kernel(None)
 
 
+@pytest.mark.timeout(240)
+def test_two_streams_segmented_chains(cg, cases):
+    """Segmented chains hand a walker from CTA to CTA through flags in global memory; a segment only ever waits for one that was
+    ticketed earlier, i.e. for a RUNNING CTA, so two such sweeps sharing the device (each wants every CTA slot) cannot deadlock
+    and must each reproduce their own result."""
+    c = cases("n57_rs0.25")
+    prev = cg.set_sweep_kernel("cta")
+    cg.set_debug(segments=True)
+    try:
+        B, S = 350, 6
+        logp = cg.make_logp(c["ktable"], c["L"])
+        reps = (B + c["x"].shape[0] - 1) // c["x"].shape[0]
+        x0 = torch.as_tensor(np.tile(c["x"], (reps, 1, 1))[:B], device="cuda")
+        si = torch.as_tensor(np.tile(c["state_idx"], (reps, 1))[:B], device="cuda")
+        pa = cg.pack_params(c["params"])
+        pb = pa.copy()
+        pb[:96] *= 1.3
+        ba, bb = logp.bind(pa, si), logp.bind(pb, si)
+        ref_a, _ = cg.mcmc(ba, x0.clone(), 5, S, 0.1)
+        ref_b, _ = cg.mcmc(bb, x0.clone(), 6, S, 0.1)
+        assert not torch.equal(ref_a, ref_b)
+        torch.cuda.synchronize()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        for _ in range(3):
+            xa, xb = x0.clone(), x0.clone()
+            torch.cuda.synchronize()
+            with torch.cuda.stream(s1):
+                cg.mcmc(ba, xa, 5, S, 0.1)
+            with torch.cuda.stream(s2):
+                cg.mcmc(bb, xb, 6, S, 0.1)
+            torch.cuda.synchronize()
+            assert torch.equal(xa, ref_a) and torch.equal(xb, ref_b)
+    finally:
+        cg.set_debug(segments=None)
+        cg.set_sweep_kernel(prev)
+
+
 def test_alternating_batch_sizes_one_process(cg, cases):
     """Launch configurations are cached per kernel instantiation; the dynamic-shared-memory attribute belongs to the function,
     not to the launch shape: a small batch (2 warps per CTA) between two large ones (4 warps per CTA) must not shrink it."""
