@@ -11,6 +11,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout(seconds): per-test limit (pytest-timeout; a no-op marker where the plugin is absent)")
 
 
 from coulombgas_b200.fixtures import load_case, load_van, CASES_2D  # noqa: E402,F401
